@@ -1,0 +1,748 @@
+// gst_b200 -- host side of the C ABI declared in include/gst_cuda.h.
+//
+// Replaces, for the decode path only, the reference's gpu/gpu.cpp + gpu/kernel_cache.cpp
+// (OpenCL context / queues / runtime kernel compilation) and the host orchestration of
+// codec/decoder.cpp:98-428.  Kernels are compiled ahead of time for sm_100a; ordering is by
+// CUDA stream instead of the reference's explicit cl_event DAG on out-of-order queues.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/gst_cuda.h"
+#include "gst_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define GST_CUDA_TRY(expr)                                                                 \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(GST_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+constexpr int kNumWorkStreams = 4;  // gpu/gpu.h:49 kMaxNumWorkQueues
+constexpr size_t kQuantum = 512;    // the reference's sub-buffer alignment quantum
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct gst_ctx {
+  int device = 0;
+  cudaStream_t streams[1 + kNumWorkStreams] = {};
+  std::atomic<uint32_t> next_stream{0};
+  // PreloadedMemory (codec/decoder.cpp:49-95): bump arena, never reset until freed
+  std::mutex arena_mutex;
+  uint8_t *arena = nullptr;
+  size_t arena_size = 0;
+  size_t arena_off = 0;
+};
+
+struct gst_ans_decoder {
+  gst_ctx *ctx = nullptr;
+  uint32_t lanes = 0;
+  uint32_t *table = nullptr;  // device, 2048 packed entries
+  uint8_t *freqs = nullptr;   // device, 512 B
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int check_header(const gst_header &h) {
+  if (h.width == 0 || h.height == 0 || (h.width % 128) || (h.height % 128))
+    return fail(GST_ERR_INVALID, "image dimensions %ux%u must be non-zero multiples of 128", h.width, h.height);
+  const uint64_t n = static_cast<uint64_t>(h.width / 4) * (h.height / 4);
+  if (n % gst::kGroupSyms)
+    return fail(GST_ERR_INVALID, "width*height/16 = %llu must be a multiple of 8192", (unsigned long long)n);
+  if (h.palette_bytes % gst::kGroupSyms)
+    return fail(GST_ERR_INVALID, "palette_bytes = %u must be a multiple of 8192", h.palette_bytes);
+  if ((h.y_cmp_sz | h.chroma_cmp_sz | h.palette_sz | h.indices_sz) & 3u)
+    return fail(GST_ERR_INVALID, "compressed stream sizes must be multiples of 4");
+  if (n > 0x7FFFFFFFull / 8) return fail(GST_ERR_INVALID, "image too large");
+  return GST_OK;
+}
+
+struct BatchLayout {
+  uint32_t n_blocks = 0, groups_per_plane = 0, max_palette = 0;
+  size_t off_region = 0, payload_bytes = 0, palette_total = 0, total_cmp = 0;
+  // scratch carve-up
+  size_t tables_off = 0, palette_off = 0, local_off = 0, total_off = 0, carry_off = 0, scratch_bytes = 0;
+};
+
+int layout_batch(const gst_header *hdrs, uint32_t n, BatchLayout *L) {
+  if (!hdrs || n == 0) return fail(GST_ERR_INVALID, "empty batch");
+  uint64_t in_total = 0, out_total = 0, pal_total = 0;
+  uint32_t max_pal = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    int rc = check_header(hdrs[i]);
+    if (rc) return rc;
+    // codec/decoder.cpp:117-121: all images of one call share their dimensions
+    if (hdrs[i].width != hdrs[0].width || hdrs[i].height != hdrs[0].height)
+      return fail(GST_ERR_INVALID, "image %u is %ux%u but image 0 is %ux%u: one call needs equal dimensions", i,
+                  hdrs[i].width, hdrs[i].height, hdrs[0].width, hdrs[0].height);
+    in_total += static_cast<uint64_t>(hdrs[i].y_cmp_sz) + hdrs[i].chroma_cmp_sz + hdrs[i].palette_sz + hdrs[i].indices_sz;
+    pal_total += hdrs[i].palette_bytes;
+    max_pal = std::max(max_pal, hdrs[i].palette_bytes);
+  }
+  const uint64_t N = static_cast<uint64_t>(hdrs[0].width / 4) * (hdrs[0].height / 4);
+  out_total = 7 * N * n + pal_total;
+  // the device-side offset table is cl_uint (codec/decoder.cpp:133-149)
+  if (in_total > 0xFFFFFFFFull || out_total > 0xFFFFFFFFull)
+    return fail(GST_ERR_INVALID, "batch of %u images overflows the 32-bit stream offsets; split it into pages", n);
+  L->n_blocks = static_cast<uint32_t>(N);
+  L->groups_per_plane = static_cast<uint32_t>(N / gst::kGroupSyms);
+  L->max_palette = max_pal;
+  L->off_region = align_up(static_cast<size_t>(n) * 8 * sizeof(uint32_t), kQuantum);
+  L->payload_bytes = static_cast<size_t>(in_total);
+  L->palette_total = static_cast<size_t>(pal_total);
+  L->total_cmp = L->off_region + static_cast<size_t>(n) * 2048 + L->payload_bytes;
+  size_t off = 0;
+  L->tables_off = off;  off += align_up(static_cast<size_t>(n) * 4 * gst::kTableSize * 4, kQuantum);
+  L->palette_off = off; off += align_up(std::max<size_t>(L->palette_total, 16), kQuantum);
+  L->local_off = off;   off += align_up(static_cast<size_t>(n) * N * 4, kQuantum);
+  L->total_off = off;   off += align_up(static_cast<size_t>(n) * L->groups_per_plane * 4, kQuantum);
+  L->carry_off = off;   off += align_up(static_cast<size_t>(n) * L->groups_per_plane * 4, kQuantum);
+  L->scratch_bytes = off;
+  return GST_OK;
+}
+
+struct Taps {
+  void *symbols = nullptr, *planes = nullptr, *indices = nullptr;
+};
+
+int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t stream, const void *cmp_dev,
+                 size_t cmp_bytes, void *out_dev, int rgb, const Taps &taps, void *const *wait_events,
+                 uint32_t n_wait, void **done_event) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  if (!cmp_dev || !out_dev) return fail(GST_ERR_INVALID, "null device buffer");
+  BatchLayout L;
+  int rc = layout_batch(hdrs, n, &L);
+  if (rc) return rc;
+  if (cmp_bytes < L.total_cmp)
+    return fail(GST_ERR_INVALID, "compressed buffer holds %zu bytes but the headers describe %zu", cmp_bytes, L.total_cmp);
+  DeviceGuard guard(ctx->device);
+  for (uint32_t i = 0; i < n_wait; ++i)
+    GST_CUDA_TRY(cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(wait_events[i]), 0));
+
+  // scratch: preallocated arena (bump, never reset) or a stream-ordered allocation
+  uint8_t *scratch = nullptr;
+  bool from_arena = false;
+  {
+    std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+    if (ctx->arena) {
+      if (ctx->arena_off + L.scratch_bytes > ctx->arena_size)
+        return fail(GST_ERR_NOMEM, "preallocated scratch exhausted: need %zu more bytes, %zu of %zu used",
+                    L.scratch_bytes, ctx->arena_off, ctx->arena_size);
+      scratch = ctx->arena + ctx->arena_off;
+      ctx->arena_off += L.scratch_bytes;
+      from_arena = true;
+    }
+  }
+  if (!from_arena) GST_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), L.scratch_bytes, stream));
+
+  gst::BatchParams p{};
+  p.cmp = static_cast<const uint8_t *>(cmp_dev);
+  p.cmp_bytes = cmp_bytes;
+  p.n_images = n;
+  p.blocks_x = hdrs[0].width / 4;
+  p.blocks_y = hdrs[0].height / 4;
+  p.n_blocks = L.n_blocks;
+  p.off_region = static_cast<uint32_t>(L.off_region);
+  p.groups_per_plane = L.groups_per_plane;
+  p.tables = reinterpret_cast<uint32_t *>(scratch + L.tables_off);
+  p.palette = scratch + L.palette_off;
+  p.palette_cap = L.palette_total;
+  p.idx_local = reinterpret_cast<int32_t *>(scratch + L.local_off);
+  p.idx_total = reinterpret_cast<int32_t *>(scratch + L.total_off);
+  p.idx_carry = reinterpret_cast<int32_t *>(scratch + L.carry_off);
+  p.out = static_cast<uint8_t *>(out_dev);
+  p.tap_symbols = static_cast<uint8_t *>(taps.symbols);
+  p.tap_planes = static_cast<int8_t *>(taps.planes);
+  p.tap_indices = static_cast<int32_t *>(taps.indices);
+
+  cudaError_t e = gst::launch_decode_batch(p, rgb, L.max_palette, stream);
+  if (!from_arena) {
+    cudaError_t e2 = cudaFreeAsync(scratch, stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (e != cudaSuccess) return fail(GST_ERR_CUDA, "decode launch failed: %s", cudaGetErrorString(e));
+  if (done_event) {
+    cudaEvent_t ev;
+    GST_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDefault));
+    GST_CUDA_TRY(cudaEventRecord(ev, stream));
+    *done_event = ev;
+  }
+  return GST_OK;
+}
+
+// ans::GenerateHistogram (ans/histogram.cpp:41-123), restated: scale counts to sum M with
+// the float rounding rule of the reference, then fix the residual one unit at a time on the
+// symbol whose code-length cost changes least (min-heap on the rank).
+struct RankedSymbol {
+  int symbol;
+  double rank;
+  bool operator>(const RankedSymbol &o) const { return rank > o.rank; }
+};
+
+double freq_change(int count, int new_count, int sign) {
+  return std::log2(static_cast<double>(new_count) / static_cast<double>(new_count + sign)) * static_cast<double>(count);
+}
+
+int normalize_frequencies(const uint32_t *counts, uint32_t n, int M, std::vector<uint32_t> *out) {
+  out->assign(n, 0);
+  int sum = 0;
+  for (uint32_t i = 0; i < n; ++i) sum = static_cast<int>(static_cast<uint32_t>(sum) + counts[i]);
+  if (sum == 0) return fail(GST_ERR_INVALID, "no symbol has a non-zero count");
+  int total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (counts[i] == 0) continue;
+    const double scaled = static_cast<float>(counts[i] * static_cast<uint32_t>(M)) / static_cast<float>(sum);
+    const int down = static_cast<int>(scaled);
+    const int pick = (scaled * scaled <= static_cast<double>(down * (down + 1))) ? down : down + 1;
+    (*out)[i] = static_cast<uint32_t>(std::max(1, pick));
+    total += static_cast<int>((*out)[i]);
+  }
+  int correction = M - total;
+  if (correction == 0) return GST_OK;
+  const int sign = correction > 0 ? 1 : -1;
+  std::vector<RankedSymbol> heap;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (counts[i] == 0) continue;
+    if ((*out)[i] > 1 || correction > 0)
+      heap.push_back({static_cast<int>(i), freq_change(static_cast<int>(counts[i]), static_cast<int>((*out)[i]), sign)});
+  }
+  std::make_heap(heap.begin(), heap.end(), std::greater<RankedSymbol>());
+  while (correction != 0) {
+    if (heap.empty()) return fail(GST_ERR_INVALID, "cannot normalise frequencies to %d", M);
+    std::pop_heap(heap.begin(), heap.end(), std::greater<RankedSymbol>());
+    const RankedSymbol s = heap.back();
+    heap.pop_back();
+    const int i = s.symbol;
+    (*out)[i] = static_cast<uint32_t>(static_cast<int>((*out)[i]) + sign);
+    correction -= sign;
+    if ((*out)[i] > 1 || sign == 1) {
+      heap.push_back({i, freq_change(static_cast<int>(counts[i]), static_cast<int>((*out)[i]), sign)});
+      std::push_heap(heap.begin(), heap.end(), std::greater<RankedSymbol>());
+    }
+  }
+  return GST_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+extern "C" {
+
+const char *gst_last_error(void) { return g_err; }
+
+int gst_ctx_create(int device, gst_ctx **out) {
+  if (!out) return fail(GST_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(GST_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(GST_ERR_INVALID, "device ordinal %d out of range [0,%d)", device, count);
+  cudaDeviceProp prop;
+  GST_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(GST_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this build contains sm_100a code only", device,
+                prop.name, prop.major, prop.minor);
+  DeviceGuard guard(device);
+  gst_ctx *ctx = new (std::nothrow) gst_ctx;
+  if (!ctx) return fail(GST_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  for (auto &s : ctx->streams) {
+    e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      gst_ctx_destroy(ctx);
+      return fail(GST_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+  }
+  // keep freed scratch in the pool so per-call cudaMallocAsync does not hit the OS
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t threshold = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  *out = ctx;
+  return GST_OK;
+}
+
+void gst_ctx_destroy(gst_ctx *ctx) {
+  if (!ctx) return;
+  DeviceGuard guard(ctx->device);
+  for (auto &s : ctx->streams)
+    if (s) {
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+    }
+  if (ctx->arena) cudaFree(ctx->arena);
+  delete ctx;
+}
+
+int gst_ctx_device(const gst_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+void *gst_stream_default(gst_ctx *ctx) { return ctx ? ctx->streams[0] : nullptr; }
+
+void *gst_stream_next(gst_ctx *ctx) {
+  if (!ctx) return nullptr;
+  return ctx->streams[1 + ctx->next_stream.fetch_add(1) % kNumWorkStreams];
+}
+
+int gst_ctx_sync(gst_ctx *ctx) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  for (auto &s : ctx->streams) GST_CUDA_TRY(cudaStreamSynchronize(s));
+  return GST_OK;
+}
+
+int gst_stream_sync(gst_ctx *ctx, void *stream) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return GST_OK;
+}
+
+int gst_malloc(gst_ctx *ctx, size_t bytes, void **dptr) {
+  if (!ctx || !dptr) return fail(GST_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  cudaError_t e = cudaMalloc(dptr, align_up(std::max<size_t>(bytes, 1), 256));
+  if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return GST_OK;
+}
+
+int gst_free(gst_ctx *ctx, void *dptr) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaFree(dptr));
+  return GST_OK;
+}
+
+int gst_host_alloc(gst_ctx *ctx, size_t bytes, void **hptr) {
+  if (!ctx || !hptr) return fail(GST_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  cudaError_t e = cudaHostAlloc(hptr, std::max<size_t>(bytes, 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return GST_OK;
+}
+
+int gst_host_free(gst_ctx *ctx, void *hptr) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaFreeHost(hptr));
+  return GST_OK;
+}
+
+int gst_upload_async(gst_ctx *ctx, void *stream, void *dst_dev, const void *src_host, size_t bytes) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return GST_OK;
+}
+
+int gst_download_async(gst_ctx *ctx, void *stream, void *dst_host, const void *src_dev, size_t bytes) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return GST_OK;
+}
+
+int gst_memset_async(gst_ctx *ctx, void *stream, void *dst_dev, int value, size_t bytes) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaMemsetAsync(dst_dev, value, bytes, static_cast<cudaStream_t>(stream)));
+  return GST_OK;
+}
+
+int gst_event_record(gst_ctx *ctx, void *stream, void **event_out) {
+  if (!ctx || !event_out) return fail(GST_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  cudaEvent_t ev;
+  GST_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDefault));
+  cudaError_t e = cudaEventRecord(ev, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    cudaEventDestroy(ev);
+    return fail(GST_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+  }
+  *event_out = ev;
+  return GST_OK;
+}
+
+int gst_event_wait(void *event) {
+  GST_CUDA_TRY(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+  return GST_OK;
+}
+
+int gst_event_elapsed_ms(void *start, void *stop, float *ms) {
+  if (!ms) return fail(GST_ERR_INVALID, "null argument");
+  GST_CUDA_TRY(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  return GST_OK;
+}
+
+void gst_event_destroy(void *event) {
+  if (event) cudaEventDestroy(static_cast<cudaEvent_t>(event));
+}
+
+// ---- stream format ---------------------------------------------------------------------
+int gst_parse_header(const uint8_t *gst, size_t len, gst_header *hdr) {
+  if (!gst || !hdr) return fail(GST_ERR_INVALID, "null argument");
+  if (len < GST_HEADER_BYTES + 4 * 512) return fail(GST_ERR_INVALID, "file of %zu bytes is too short for a .gst header", len);
+  memcpy(hdr, gst, GST_HEADER_BYTES);
+  int rc = check_header(*hdr);
+  if (rc) return rc;
+  const uint64_t need = static_cast<uint64_t>(GST_HEADER_BYTES) + 2048 + hdr->y_cmp_sz + hdr->chroma_cmp_sz +
+                        hdr->palette_sz + hdr->indices_sz;
+  if (need > len) return fail(GST_ERR_INVALID, "header describes %llu bytes but the file has %zu", (unsigned long long)need, len);
+  // every stream starts with one u32 end offset per group
+  const uint64_t n = static_cast<uint64_t>(hdr->width / 4) * (hdr->height / 4);
+  const uint64_t groups[4] = {2 * n / gst::kGroupSyms, 4 * n / gst::kGroupSyms, hdr->palette_bytes / gst::kGroupSyms,
+                              n / gst::kGroupSyms};
+  const uint32_t sizes[4] = {hdr->y_cmp_sz, hdr->chroma_cmp_sz, hdr->palette_sz, hdr->indices_sz};
+  for (int s = 0; s < 4; ++s)
+    if (sizes[s] < groups[s] * (4 + 4 * gst::kLanes))
+      return fail(GST_ERR_INVALID, "stream %d of %u bytes cannot hold %llu groups", s, sizes[s], (unsigned long long)groups[s]);
+  return GST_OK;
+}
+
+size_t gst_packed_size(const gst_header *hdrs, uint32_t n) {
+  BatchLayout L;
+  if (layout_batch(hdrs, n, &L)) return 0;
+  return L.total_cmp;
+}
+
+int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint8_t *dst, size_t dst_cap,
+                   gst_header *hdrs_out) {
+  if (!gst_files || !lens || !dst || !hdrs_out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
+  for (uint32_t i = 0; i < n; ++i) {
+    int rc = gst_parse_header(gst_files[i], lens[i], &hdrs_out[i]);
+    if (rc) return rc;
+  }
+  BatchLayout L;
+  int rc = layout_batch(hdrs_out, n, &L);
+  if (rc) return rc;
+  if (dst_cap < L.total_cmp) return fail(GST_ERR_SMALL, "packed batch needs %zu bytes, buffer has %zu", L.total_cmp, dst_cap);
+  uint32_t *out_off = reinterpret_cast<uint32_t *>(dst);
+  uint32_t *in_off = out_off + 4 * n;
+  memset(dst, 0, L.off_region);
+  uint8_t *freqs = dst + L.off_region;
+  uint8_t *payload = freqs + static_cast<size_t>(n) * 2048;
+  uint32_t in_acc = 0, out_acc = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const gst_header &h = hdrs_out[i];
+    const uint32_t N = L.n_blocks;
+    const uint32_t in_sz[4] = {h.y_cmp_sz, h.chroma_cmp_sz, h.palette_sz, h.indices_sz};
+    const uint32_t out_sz[4] = {2 * N, 4 * N, h.palette_bytes, N};
+    const uint8_t *src = gst_files[i] + GST_HEADER_BYTES;
+    memcpy(freqs + static_cast<size_t>(i) * 2048, src, 2048);
+    const size_t body = static_cast<size_t>(in_sz[0]) + in_sz[1] + in_sz[2] + in_sz[3];
+    memcpy(payload + in_acc, src + 2048, body);
+    for (int s = 0; s < 4; ++s) {
+      in_off[4 * i + s] = in_acc;
+      out_off[4 * i + s] = out_acc;
+      in_acc += in_sz[s];
+      out_acc += out_sz[s];
+    }
+  }
+  return GST_OK;
+}
+
+// ---- scratch ---------------------------------------------------------------------------
+size_t gst_required_scratch(const gst_header *hdr) {
+  if (!hdr) return 0;
+  // codec/decoder.cpp:41-47
+  return 4 * static_cast<size_t>(gst::kTableSize) * 6 + 17 * static_cast<size_t>(hdr->width) * hdr->height / 16 +
+         hdr->palette_bytes;
+}
+
+int gst_preallocate(gst_ctx *ctx, size_t bytes) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+  if (ctx->arena) {
+    GST_CUDA_TRY(cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+  }
+  ctx->arena_size = ctx->arena_off = 0;
+  // every region is rounded up to the 512-byte quantum: leave room for that
+  const size_t padded = align_up(bytes, kQuantum) + 16 * kQuantum;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->arena), padded);
+  if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", padded, cudaGetErrorString(e));
+  ctx->arena_size = padded;
+  return GST_OK;
+}
+
+int gst_free_scratch(gst_ctx *ctx) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+  if (ctx->arena) GST_CUDA_TRY(cudaFree(ctx->arena));
+  ctx->arena = nullptr;
+  ctx->arena_size = ctx->arena_off = 0;
+  return GST_OK;
+}
+
+// ---- decode ----------------------------------------------------------------------------
+int gst_load_dxt_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, void *stream, const void *cmp_dev,
+                       size_t cmp_bytes, void *out_dev, void *const *wait_events, uint32_t n_wait, void **done_event) {
+  return decode_batch(ctx, hdrs, n, static_cast<cudaStream_t>(stream), cmp_dev, cmp_bytes, out_dev, 0, Taps{},
+                      wait_events, n_wait, done_event);
+}
+
+int gst_load_rgb_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, void *stream, const void *cmp_dev,
+                       size_t cmp_bytes, void *out_dev, void *const *wait_events, uint32_t n_wait, void **done_event) {
+  return decode_batch(ctx, hdrs, n, static_cast<cudaStream_t>(stream), cmp_dev, cmp_bytes, out_dev, 1, Taps{},
+                      wait_events, n_wait, done_event);
+}
+
+int gst_load_dxt_batch_tapped(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, void *stream, const void *cmp_dev,
+                              size_t cmp_bytes, void *out_dev, void *symbols_dev, void *planes_dev, void *indices_dev) {
+  Taps t;
+  t.symbols = symbols_dev;
+  t.planes = planes_dev;
+  t.indices = indices_dev;
+  return decode_batch(ctx, hdrs, n, static_cast<cudaStream_t>(stream), cmp_dev, cmp_bytes, out_dev, 0, t, nullptr, 0,
+                      nullptr);
+}
+
+int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n,
+                              uint32_t page, int mode, uint8_t *out, size_t out_cap) {
+  if (!ctx || !gst_files || !lens || !out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
+  if (page == 0 || page > n) page = n;
+  DeviceGuard guard(ctx->device);
+  gst_header h0;
+  int rc = gst_parse_header(gst_files[0], lens[0], &h0);
+  if (rc) return rc;
+  const size_t per_image = mode ? static_cast<size_t>(h0.width) * h0.height * 3 : static_cast<size_t>(h0.width) * h0.height / 2;
+  if (out_cap < per_image * n) return fail(GST_ERR_SMALL, "output needs %zu bytes, buffer has %zu", per_image * n, out_cap);
+
+  // one slot per work stream: pinned staging + device input + device output, sized for the
+  // largest page; a slot is reused once the stream that owns it has drained
+  struct Slot {
+    uint8_t *pinned = nullptr, *d_in = nullptr, *d_out = nullptr;
+    size_t cap_in = 0;
+    cudaStream_t stream = nullptr;
+  };
+  const uint32_t n_pages = (n + page - 1) / page;
+  const uint32_t n_slots = std::min<uint32_t>(kNumWorkStreams, n_pages);
+  std::vector<Slot> slots(n_slots);
+  std::vector<gst_header> hdrs(page);
+  auto cleanup = [&]() {
+    for (auto &s : slots) {
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      if (s.pinned) cudaFreeHost(s.pinned);
+      if (s.d_in) cudaFree(s.d_in);
+      if (s.d_out) cudaFree(s.d_out);
+    }
+  };
+  for (uint32_t pg = 0; pg < n_pages; ++pg) {
+    Slot &s = slots[pg % n_slots];
+    const uint32_t first = pg * page, cnt = std::min(page, n - first);
+    if (!s.stream) s.stream = ctx->streams[1 + pg % n_slots];
+    size_t raw = 0;
+    for (uint32_t i = 0; i < cnt; ++i) raw += lens[first + i];
+    const size_t need = align_up(static_cast<size_t>(cnt) * 32, kQuantum) + raw;  // upper bound on the packed size
+    cudaError_t e = cudaStreamSynchronize(s.stream);  // previous page of this slot is done
+    if (e == cudaSuccess && need > s.cap_in) {
+      if (s.pinned) cudaFreeHost(s.pinned);
+      if (s.d_in) cudaFree(s.d_in);
+      s.pinned = s.d_in = nullptr;
+      s.cap_in = align_up(need + need / 4, 4096);
+      e = cudaHostAlloc(reinterpret_cast<void **>(&s.pinned), s.cap_in, cudaHostAllocDefault);
+      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in);
+    }
+    if (e == cudaSuccess && !s.d_out) e = cudaMalloc(reinterpret_cast<void **>(&s.d_out), per_image * page);
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(GST_ERR_CUDA, "staging allocation failed: %s", cudaGetErrorString(e));
+    }
+    rc = gst_pack_batch(gst_files + first, lens + first, cnt, s.pinned, s.cap_in, hdrs.data());
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+    const size_t packed = gst_packed_size(hdrs.data(), cnt);
+    e = cudaMemcpyAsync(s.d_in, s.pinned, packed, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) {
+      rc = decode_batch(ctx, hdrs.data(), cnt, s.stream, s.d_in, s.cap_in, s.d_out, mode, Taps{}, nullptr, 0, nullptr);
+      if (rc) {
+        cleanup();
+        return rc;
+      }
+      e = cudaMemcpyAsync(out + per_image * first, s.d_out, per_image * cnt, cudaMemcpyDeviceToHost, s.stream);
+    }
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(GST_ERR_CUDA, "page %u failed: %s", pg, cudaGetErrorString(e));
+    }
+  }
+  cudaError_t e = cudaSuccess;
+  for (auto &s : slots) {
+    cudaError_t e2 = cudaStreamSynchronize(s.stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  cleanup();
+  if (e != cudaSuccess) return fail(GST_ERR_CUDA, "decode failed: %s", cudaGetErrorString(e));
+  return GST_OK;
+}
+
+int gst_decompress_host(gst_ctx *ctx, const uint8_t *gst, size_t len, int mode, uint8_t *out, size_t out_cap) {
+  const uint8_t *files[1] = {gst};
+  const size_t lens[1] = {len};
+  return gst_decompress_host_batch(ctx, files, lens, 1, 1, mode, out, out_cap);
+}
+
+// ---- standalone rANS decoder -----------------------------------------------------------
+int gst_normalize_frequencies(const uint32_t *counts, uint32_t n, uint32_t *out) {
+  if (!counts || !out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
+  std::vector<uint32_t> h;
+  int rc = normalize_frequencies(counts, n, gst::kTableSize, &h);
+  if (rc) return rc;
+  memcpy(out, h.data(), n * sizeof(uint32_t));
+  return GST_OK;
+}
+
+int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t n_tables, void *tables_dev) {
+  if (!ctx || !freqs_dev || !tables_dev) return fail(GST_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(gst::launch_build_tables(static_cast<const uint8_t *>(freqs_dev), n_tables,
+                                        static_cast<uint32_t *>(tables_dev), static_cast<cudaStream_t>(stream)));
+  return GST_OK;
+}
+
+int gst_ans_rebuild(gst_ans_decoder *d, const uint32_t *F, uint32_t n) {
+  if (!d || !F || n == 0 || n > 256) return fail(GST_ERR_INVALID, "need 1..256 symbol counts");
+  std::vector<uint32_t> h;
+  int rc = normalize_frequencies(F, n, gst::kTableSize, &h);
+  if (rc) return rc;
+  uint16_t f16[256] = {0};
+  for (uint32_t i = 0; i < n; ++i) f16[i] = static_cast<uint16_t>(h[i]);
+  DeviceGuard guard(d->ctx->device);
+  cudaStream_t s = d->ctx->streams[0];
+  // pageable source: the copy is staged before the call returns
+  GST_CUDA_TRY(cudaMemcpyAsync(d->freqs, f16, sizeof(f16), cudaMemcpyHostToDevice, s));
+  GST_CUDA_TRY(gst::launch_build_tables(d->freqs, 1, d->table, s));
+  GST_CUDA_TRY(cudaStreamSynchronize(s));
+  return GST_OK;
+}
+
+int gst_ans_create(gst_ctx *ctx, const uint32_t *F, uint32_t n, uint32_t lanes, gst_ans_decoder **out) {
+  if (!ctx || !out) return fail(GST_ERR_INVALID, "null argument");
+  if (lanes == 0 || lanes > gst::kLanes) return fail(GST_ERR_INVALID, "lanes must be 1..32");
+  DeviceGuard guard(ctx->device);
+  gst_ans_decoder *d = new (std::nothrow) gst_ans_decoder;
+  if (!d) return fail(GST_ERR_NOMEM, "out of host memory");
+  d->ctx = ctx;
+  d->lanes = lanes;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d->table), gst::kTableSize * 4);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d->freqs), 512);
+  if (e != cudaSuccess) {
+    gst_ans_destroy(d);
+    return fail(GST_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  int rc = gst_ans_rebuild(d, F, n);
+  if (rc) {
+    gst_ans_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return GST_OK;
+}
+
+int gst_ans_table(gst_ans_decoder *d, uint8_t *symbols, uint16_t *freqs, uint16_t *cum_freqs) {
+  if (!d) return fail(GST_ERR_INVALID, "null decoder");
+  DeviceGuard guard(d->ctx->device);
+  std::vector<uint32_t> t(gst::kTableSize);
+  GST_CUDA_TRY(cudaMemcpy(t.data(), d->table, t.size() * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t slot = 0; slot < gst::kTableSize; ++slot) {
+    const uint32_t e = t[slot];
+    if (symbols) symbols[slot] = static_cast<uint8_t>(e & 0xFF);
+    if (freqs) freqs[slot] = static_cast<uint16_t>((e >> 8) & 0xFFF);
+    if (cum_freqs) cum_freqs[slot] = static_cast<uint16_t>(slot - (e >> 20));
+  }
+  return GST_OK;
+}
+
+int gst_ans_decode(gst_ans_decoder *d, uint32_t lanes, const uint32_t *states, const uint8_t *const *data,
+                   const size_t *data_len, uint32_t groups, uint8_t *out) {
+  if (!d || !states || !data || !data_len || !out) return fail(GST_ERR_INVALID, "null argument");
+  if (lanes == 0 || lanes > d->lanes) return fail(GST_ERR_INVALID, "lanes must be 1..%u", d->lanes);
+  if (groups == 0) return GST_OK;
+  // the layout ans/ans_ocl.cpp:283-313 builds: [u32 end offsets][pad | words | states]...
+  const size_t head = align_up(4 * static_cast<size_t>(groups), 4);
+  std::vector<uint8_t> host;
+  std::vector<uint32_t> offsets(groups);
+  size_t pos = head;
+  for (uint32_t g = 0; g < groups; ++g) {
+    if (data_len[g] & 1) return fail(GST_ERR_INVALID, "group %u: renorm data must be a whole number of 16-bit words", g);
+    pos += align_up(data_len[g], 4) + 4 * static_cast<size_t>(lanes);
+    offsets[g] = static_cast<uint32_t>(pos);
+  }
+  const size_t total = align_up(pos, 16);
+  host.assign(total, 0);
+  memcpy(host.data(), offsets.data(), 4 * static_cast<size_t>(groups));
+  for (uint32_t g = 0; g < groups; ++g) {
+    uint8_t *end = host.data() + offsets[g];
+    memcpy(end - 4 * lanes, states + static_cast<size_t>(g) * lanes, 4 * static_cast<size_t>(lanes));
+    memcpy(end - 4 * lanes - data_len[g], data[g], data_len[g]);
+  }
+  DeviceGuard guard(d->ctx->device);
+  cudaStream_t s = d->ctx->streams[0];
+  const size_t slack = 0;
+  uint8_t *dbuf = nullptr, *dout = nullptr;
+  const size_t out_bytes = static_cast<size_t>(groups) * lanes * gst::kSymsPerLane;
+  GST_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&dbuf), slack + total));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dout), out_bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dbuf + slack, host.data(), total, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = gst::launch_ans_decode_plain(d->table, dbuf + slack, total, groups, lanes, dout, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(dbuf);
+  if (dout) cudaFree(dout);
+  if (e != cudaSuccess) return fail(GST_ERR_CUDA, "ans decode failed: %s", cudaGetErrorString(e));
+  return GST_OK;
+}
+
+void gst_ans_destroy(gst_ans_decoder *d) {
+  if (!d) return;
+  DeviceGuard guard(d->ctx->device);
+  if (d->table) cudaFree(d->table);
+  if (d->freqs) cudaFree(d->freqs);
+  delete d;
+}
+
+int gst_launches_per_batch(void) { return gst::kLaunchesPerBatch; }
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// gst_b200 -- device-side declarations shared by the kernels and the C-ABI host layer.
+//
+// The decode path of GammaUNC/GST (.gst stream -> DXT1 blocks), rewritten for sm_100a.
+// Reference stages (citations relative to the reference tree):
+//   1. ans/build_table.cl:12-83           -> build_tables_kernel
+//   2. ans/ans_decode.cl:25-143           -> rans_decode_group() inside every decode kernel
+//   3. codec/decode_indices.cl:6-84       -> index_stream_kernel (scan fused behind the rANS warp)
+//   4. codec/inverse_wavelet.cl:69-192    -> fused_planes_kernel, phase 2
+//   5. codec/assemble.cl:64-129           -> fused_planes_kernel, phase 3
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gst {
+
+constexpr int kTableLog = 11;                 // ans/ans.h:73 kANSTableSize = 1 << 11
+constexpr int kTableSize = 1 << kTableLog;
+constexpr int kSymsPerLane = 256;             // ans/ans.h:74 kNumEncodedSymbols
+constexpr int kLanes = 32;                    // ans/ans.h:75 kThreadsPerEncodingGroup
+constexpr int kGroupSyms = kSymsPerLane * kLanes;
+constexpr uint32_t kRansL = 16u << kTableLog; // ans/ans_decode.cl:7-8  k*M = 2^15
+constexpr int kTile = 32;                     // codec/codec_base.h:22 kWaveletBlockDim
+constexpr int kTileSyms = kTile * kTile;
+
+// Packed decode-table entry (internal scratch format, 4 B instead of the reference's
+// 6 B AnsTableEntry, codec/decoder.cpp:20-24):  sym | freq << 8 | (slot - cum_freq) << 20,
+// so that  state' = (state >> 11) * freq + bias  needs no separate cum_freq / slot add.
+__host__ __device__ inline uint32_t pack_entry(uint32_t sym, uint32_t freq, uint32_t bias) {
+  return (sym & 0xFFu) | ((freq & 0xFFFu) << 8) | (bias << 20);
+}
+
+// Geometry + buffer description of one LoadCompressedDXTs-style call.  The compressed
+// buffer keeps the reference's device layout (codec/decoder.cpp:153-209, 430-476;
+// demo/photos_sf.cpp:753-795):
+//   [u32 out_off[4B]][u32 in_off[4B]] pad to 512 | B x 4 x 512 B freqs | payloads
+struct BatchParams {
+  const uint8_t *cmp;        // device, start of the offsets region
+  uint64_t cmp_bytes;        // bytes readable from cmp
+  uint32_t n_images;         // B
+  uint32_t blocks_x, blocks_y;
+  uint32_t n_blocks;         // N = blocks_x * blocks_y
+  uint32_t off_region;       // bytes of the (padded) offsets region
+  uint32_t groups_per_plane; // N / 8192
+  // scratch
+  uint32_t *tables;          // [B][4][2048] packed entries
+  uint8_t *palette;          // compact: image b at pal_off(b) = out_off[4b+2] - 7N*b - 6N
+  uint64_t palette_cap;      // bytes available in `palette`
+  int32_t *idx_local;        // [B][N]   group-local inclusive prefix of (delta - 128)
+  int32_t *idx_total;        // [B][N/8192] sum of every index group
+  int32_t *idx_carry;        // [B][N/8192] exclusive scan of idx_total
+  // outputs
+  uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
+  // optional taps for the stage parity tests (NULL in production)
+  uint8_t *tap_symbols;      // reference decmp_buf layout: image b stream s at out_off[4b+s]
+  int8_t *tap_planes;        // [B][6][N] raster planes (codec/decoder.cpp:280)
+  int32_t *tap_indices;      // [B][N] final palette indices (codec/decoder.cpp:302)
+};
+
+// launch helpers (gst_kernels.cu)
+cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,
+                                cudaStream_t s);
+// max_palette_bytes = max over the batch of GenTCHeader::palette_bytes (sizes the grid)
+cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,
+                                cudaStream_t s);
+cudaError_t launch_ans_decode_plain(const uint32_t *table, const uint8_t *data,
+                                    uint64_t data_bytes, uint32_t n_groups, uint32_t n_lanes,
+                                    uint8_t *out, cudaStream_t s);
+// number of kernels launch_decode_batch enqueues (for bench.py's gpu_launches)
+constexpr int kLaunchesPerBatch = 4;
+
+}  // namespace gst
