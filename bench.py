@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the .gst -> DXT1 decode path (BASELINE.json metric: decoded GTexel/s and
+compressed GB/s per B200 and at 2/4/8 GPUs, against the HBM roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU decode
+
+A step is one LoadCompressedDXTs-style call over the whole workload (default: BASELINE.json
+configs[3], a batch of 1024 2048x2048 textures per GPU; --config picks another).  Inputs
+are reference-encoded .gst streams of seeded synthetic images (`--distinct` different images,
+tiled to the batch size); they are resident in HBM when the timed region starts.  The `e2e`
+figure runs the same workload through gst_decompress_host_batch with pinned HOST buffers:
+host packing, H2D, decode and D2H of every DXT1 block inside the timed region.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# BASELINE.json configs (index = position in "configs"): (width, height, images per GPU, name)
+CONFIGS = {
+    0: (512, 512, 1, "configs[0]: single 512x512 texture"),
+    1: (512, 512, 128, "configs[1]: batch of 128 512x512 textures"),
+    2: (4096, 4096, 1, "configs[2]: single 4096x4096 texture"),
+    3: (2048, 2048, 1024, "configs[3]: batch of 1024 2048x2048 textures"),
+    4: (1920, 1024, 600, "configs[4]: 600 frames 1920x1024"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", type=int, default=3, help="index into BASELINE.json configs")
+    ap.add_argument("--images", type=int, default=0, help="override images per GPU")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct encoded images tiled to the batch")
+    ap.add_argument("--page", type=int, default=32, help="images per page on the e2e path")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def load_streams(cfg_id, width, height, distinct, rank, world):
+    """`distinct` reference-encoded streams of seeded synthetic images (seed = config*10000+i,
+    SURVEY.md section 8d).  Rank 0 encodes what the cache lacks; the others wait."""
+    import gst_fixtures as fx
+    seeds = [cfg_id * 10000 + i for i in range(distinct)]
+    if world > 1:
+        import torch.distributed as dist
+        if rank == 0:
+            fx.encode_images(width, height, seeds)
+        dist.barrier()
+    streams = fx.encode_images(width, height, seeds)
+    return [g for g, _ in streams], [d for _, d in streams]
+
+
+def cpu_decode_rate(files, sample, threads):
+    """Reference CPU decode (oracle/_ref: ans/decode.cpp + codec/wavelet.cpp linked unmodified,
+    scan/assembly restated) of `sample` images on `threads` host threads.  Returns
+    (seconds, kind).  Falls back to the plain-C port when the reference library is absent."""
+    import gst_fixtures as fx
+    L = fx.ref()
+    hdr = fx.header_of(files[0])
+    per = hdr["width"] * hdr["height"] // 2
+    n = sample
+    outs = [np.empty(per, dtype=np.uint8) for _ in range(min(n, 4 * threads))]
+    if L is not None:
+        ptrs = (C.c_void_p * n)(*[files[i % len(files)].ctypes.data for i in range(n)])
+        lens = (C.c_size_t * n)(*[files[i % len(files)].size for i in range(n)])
+        optr = (C.c_void_p * n)(*[outs[i % len(outs)].ctypes.data for i in range(n)])
+        t0 = time.perf_counter()
+        failed = L.gstref_decode_batch(ptrs, lens, n, optr, threads)
+        dt = time.perf_counter() - t0
+        assert failed == 0, f"{failed} reference decodes failed"
+        return dt, "reference"
+    O = fx.oracle()
+    t0 = time.perf_counter()
+    work = list(range(n))
+    lock = threading.Lock()
+
+    def run():
+        out = np.empty(per, dtype=np.uint8)
+        while True:
+            with lock:
+                if not work:
+                    return
+                i = work.pop()
+            f = files[i % len(files)]
+            O.gsto_decode(f.ctypes.data, f.size, 0, out.ctypes.data, None, None, None)  # ctypes drops the GIL
+
+    ts = [threading.Thread(target=run) for _ in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return time.perf_counter() - t0, "port"
+
+
+def run_reference(args, rank, world, cfg):
+    width, height, images, name = cfg
+    if rank != 0:
+        return
+    files, _ = load_streams(args.config, width, height, min(args.distinct, max(images, 1)), 0, 1)
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or max(1, min(images, 2 * threads))
+    for _ in range(args.warmup):
+        cpu_decode_rate(files, sample, threads)
+    total, kind = 0.0, "reference"
+    for _ in range(args.steps):
+        dt, kind = cpu_decode_rate(files, sample, threads)
+        total += dt
+    texels = float(width) * height * sample * args.steps
+    cmp_bytes = float(sum(files[i % len(files)].size - 28 for i in range(sample))) * args.steps
+    val = texels / total / 1e9
+    line = {
+        "impl": "reference", "metric": "decoded GTexel/s (.gst -> DXT1)", "value": val, "unit": "GTexel/s",
+        "compressed_gb_s": cmp_bytes / total / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/i32", "data": "synthetic",
+        "config": {"workload": name, "width": width, "height": height,
+                   "note": "CPU decode of a bounded sample per step, host memory only"},
+        "cpu_baseline": {"value": val, "unit": "GTexel/s", "cores": threads, "kind": kind,
+                         "sample": f"{sample} images of {width}x{height} per step, one image per task"},
+        "e2e": {"value": val, "unit": "GTexel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    cfg = CONFIGS[args.config]
+    if args.images:
+        cfg = (cfg[0], cfg[1], args.images, cfg[3] + f" (images per GPU overridden to {args.images})")
+    if args.impl == "reference":
+        run_reference(args, rank, world, cfg)
+        return
+    width, height, images, name = cfg
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    import gst_b200
+    import gst_fixtures as fx
+    from gst_b200.capi import check, lib
+
+    dec = gst_b200.Decoder(local_rank)
+    distinct = min(args.distinct, images)
+    files, goldens = load_streams(args.config, width, height, distinct, rank, world)
+    order = [(i + rank) % distinct for i in range(images)]  # ranks start at different images
+    batch = [files[j] for j in order]
+
+    # ---- device-resident inputs ---------------------------------------------------------
+    packed, hdrs = gst_b200.pack_batch(batch)
+    N = hdrs[0].num_blocks
+    d_cmp, d_out = dec.malloc(packed.size), dec.malloc(8 * N * images)
+    dec.upload(d_cmp, packed)
+    stream = dec.GetDefaultCommandQueue()
+    harr = (gst_b200.capi.gst_header * images)(*[h.to_c() for h in hdrs])
+
+    def step():
+        check(lib().gst_load_dxt_batch(dec.ctx, harr, images, stream, d_cmp.ptr, d_cmp.nbytes, d_out.ptr, None, 0, None))
+
+    # ---- parity before timing: every distinct image against the CPU oracle ----------------
+    dec.memset(d_out, 0xEE)
+    step()
+    dec.sync(stream)
+    checked = 0
+    for pos in range(min(distinct, images)):
+        got = dec.download(d_out, 8 * N, offset=pos * 8 * N)
+        j = order[pos]
+        if pos < 2:
+            want = fx.oracle_decode(files[j], taps=False)["out"]
+            assert np.array_equal(got, want), f"image {pos}: CUDA output differs from the CPU oracle"
+        assert np.array_equal(got, goldens[j]), f"image {pos}: CUDA output differs from the encoder's PhysicalBlocks()"
+        checked += 1
+    last = dec.download(d_out, 8 * N, offset=(images - 1) * 8 * N)
+    assert np.array_equal(last, goldens[order[-1]]), "last image of the batch differs"
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    dec.sync(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        dec.sync()
+
+    # ---- timed region: K steps, CUDA events on the launching stream -----------------------
+    dec.profile(True)
+    barrier()
+    ev0 = dec.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1 = dec.record(stream)
+    ev1.wait()
+    barrier()
+    dec.profile(False)
+    ms_total = ev0.elapsed_ms(ev1)
+    kernel_ms, calls = dec.profile_read()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    texels_rank = float(width) * height * images
+    cmp_rank = float(sum(f.size - 28 for f in batch))
+    alg_bytes_rank = cmp_rank + 8.0 * N * images  # (file - 28) + W*H/2 per image
+
+    # ---- end to end: host .gst buffers -> host DXT1 blocks ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin_files = []
+        for f in files:
+            pb = dec.pinned(f.size)
+            pb.array[:] = f
+            pin_files.append(pb)
+        pin_out = dec.pinned(8 * N * images)
+        ptrs = (C.c_void_p * images)(*[pin_files[j].ptr for j in order])
+        lens = (C.c_size_t * images)(*[files[j].size for j in order])
+
+        def e2e_step():
+            check(lib().gst_decompress_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, pin_out.ptr, pin_out.nbytes))
+
+        e2e_step()  # warm-up: grows the staging buffers
+        assert np.array_equal(pin_out.array[: 8 * N], goldens[order[0]]), "e2e output differs"
+        assert np.array_equal(pin_out.array[(images - 1) * 8 * N:], goldens[order[-1]]), "e2e output differs"
+        e2e_steps = args.e2e_steps or max(1, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": texels_rank * world * e2e_steps / dt / 1e9, "unit": "GTexel/s",
+               "h2d_bytes_per_step": int(packed.size) * world, "d2h_bytes_per_step": int(8 * N * images) * world,
+               "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
+               "compressed_gb_s": cmp_rank * world * e2e_steps / dt / 1e9,
+               "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
+    clocks = sampler.stop()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        per_image_s = 0.11 * (width * height) / (2048.0 * 2048.0)  # survey probe, one core
+        sample = args.cpu_sample or int(max(1, min(images, 15.0 / max(per_image_s, 1e-4))))
+        dt, kind = cpu_decode_rate(files, sample, threads)
+        cpu = {"value": float(width) * height * sample / dt / 1e9, "unit": "GTexel/s", "cores": threads, "kind": kind,
+               "sample": f"{sample} images of {width}x{height} ({distinct} distinct), one image per task, {dt:.2f} s wall"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        # dominant kernel: fused_planes (Y + chroma rANS, wavelet, assembly).  Its algorithmic
+        # bytes: the Y and chroma streams + their two 512-byte freq tables read once, the DXT1
+        # blocks written once.
+        fused_bytes = float(sum(h.y_cmp_sz + h.chroma_cmp_sz + 1024 for h in hdrs)) + 8.0 * N * images
+        fused_ms = kernel_ms["fused_planes"] / max(calls, 1)
+        achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
+        step_gbs = alg_bytes_rank / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": "decoded GTexel/s (.gst -> DXT1)", "value": texels_rank * world / (ms_step * 1e-3) / 1e9,
+            "unit": "GTexel/s", "compressed_gb_s": cmp_rank * world / (ms_step * 1e-3) / 1e9,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (integer only)",
+            "data": "synthetic",
+            "config": {"workload": name, "width": width, "height": height, "images_per_gpu": images,
+                       "distinct_images": distinct, "bits_per_texel": 8.0 * cmp_rank / texels_rank,
+                       "sharding": "independent images per rank, no data-path collective",
+                       "l2": "inputs+outputs per step exceed the 126 MB L2" if alg_bytes_rank > 2 * 126e6 else
+                             "working set fits L2 (latency-bound config)",
+                       "parity": f"{checked} distinct images + last checked bit-exact before timing"},
+            "roofline": {"bound": "hbm", "kernel": "fused_planes_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "kernel_ms": fused_ms, "kernel_bytes": fused_bytes,
+                         "step_achieved": step_gbs, "step_frac": step_gbs / peak,
+                         "kernel_ms_all": {k: v / max(calls, 1) for k, v in kernel_ms.items()}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": lib().gst_launches_per_batch() * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    dec.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,7 @@ PROTOTYPES = {
     "gst_decompress_host": (_int, [_vp, _vp, _sz, _int, _vp, _sz]),
     "gst_decompress_host_batch": (_int, [_vp, _pp, C.POINTER(_sz), _u32, _u32, _int, _vp, _sz]),
     "gst_load_dxt_batch_tapped": (_int, [_vp, _hdr_p, _u32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
-    "gst_normalize_frequencies": (_int, [C.POINTER(_u32), _u32, C.POINTER(_u32)]),
+    "gst_normalize_frequencies": (_int, [C.POINTER(_u32), _u32, _u32, C.POINTER(_u32)]),
     "gst_ans_create": (_int, [_vp, C.POINTER(_u32), _u32, _u32, _pp]),
     "gst_ans_rebuild": (_int, [_vp, C.POINTER(_u32), _u32]),
     "gst_ans_table": (_int, [_vp, _vp, _vp, _vp]),
@@ -62,6 +62,8 @@ PROTOTYPES = {
     "gst_ans_destroy": (None, [_vp]),
     "gst_build_tables": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "gst_launches_per_batch": (_int, []),
+    "gst_profile_enable": (_int, [_vp, _int]),
+    "gst_profile_read": (_int, [_vp, C.POINTER(C.c_double), _u32, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -13,6 +13,8 @@
 #include <functional>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gst_cuda.h"
@@ -54,6 +56,18 @@ struct gst_ctx {
   uint8_t *arena = nullptr;
   size_t arena_size = 0;
   size_t arena_off = 0;
+  // staging of gst_decompress_host_batch, one slot per work stream, grow-only
+  std::mutex host_batch_mutex;
+  struct HostSlotT {
+    uint8_t *pinned[2] = {nullptr, nullptr};
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    size_t cap_in = 0, cap_out = 0;
+  } host_slots[kNumWorkStreams];
+  // optional per-kernel timing (gst_profile_*): events around every kernel of every call
+  std::mutex prof_mutex;
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;  // (kLaunchesPerBatch + 1) per recorded call
 };
 
 struct gst_ans_decoder {
@@ -64,6 +78,8 @@ struct gst_ans_decoder {
 };
 
 namespace {
+
+using HostSlot = gst_ctx::HostSlotT;
 
 struct DeviceGuard {
   int prev = -1;
@@ -190,7 +206,19 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.tap_planes = static_cast<int8_t *>(taps.planes);
   p.tap_indices = static_cast<int32_t *>(taps.indices);
 
-  cudaError_t e = gst::launch_decode_batch(p, rgb, L.max_palette, stream);
+  cudaEvent_t marks[gst::kLaunchesPerBatch + 1];
+  bool profiled = false;
+  {
+    std::lock_guard<std::mutex> lock(ctx->prof_mutex);
+    profiled = ctx->prof_on;
+  }
+  if (profiled)
+    for (auto &m : marks) GST_CUDA_TRY(cudaEventCreateWithFlags(&m, cudaEventDefault));
+  cudaError_t e = gst::launch_decode_batch(p, rgb, L.max_palette, stream, profiled ? marks : nullptr);
+  if (profiled) {
+    std::lock_guard<std::mutex> lock(ctx->prof_mutex);
+    ctx->prof_events.insert(ctx->prof_events.end(), marks, marks + gst::kLaunchesPerBatch + 1);
+  }
   if (!from_arena) {
     cudaError_t e2 = cudaFreeAsync(scratch, stream);
     if (e == cudaSuccess) e = e2;
@@ -309,6 +337,15 @@ void gst_ctx_destroy(gst_ctx *ctx) {
       cudaStreamDestroy(s);
     }
   if (ctx->arena) cudaFree(ctx->arena);
+  for (auto &hs : ctx->host_slots) {
+    for (int k = 0; k < 2; ++k) {
+      if (hs.pinned[k]) cudaFreeHost(hs.pinned[k]);
+      if (hs.h2d_done[k]) cudaEventDestroy(hs.h2d_done[k]);
+    }
+    if (hs.d_in) cudaFree(hs.d_in);
+    if (hs.d_out) cudaFree(hs.d_out);
+  }
+  for (auto ev : ctx->prof_events) cudaEventDestroy(ev);
   delete ctx;
 }
 
@@ -537,84 +574,104 @@ int gst_load_dxt_batch_tapped(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, 
                       nullptr);
 }
 
+// Host-to-host batch decode.  The batch is cut into pages (demo/photos_sf.cpp:688); page k is
+// handled by work stream k % 4 and by one host thread per stream: the thread packs the page
+// into pinned staging (two buffers per stream, so packing page k+4 overlaps the transfers of
+// page k), then enqueues H2D -> decode -> D2H on its stream.  Staging lives in the context
+// and only grows.
 int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n,
                               uint32_t page, int mode, uint8_t *out, size_t out_cap) {
   if (!ctx || !gst_files || !lens || !out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
   if (page == 0 || page > n) page = n;
-  DeviceGuard guard(ctx->device);
   gst_header h0;
   int rc = gst_parse_header(gst_files[0], lens[0], &h0);
   if (rc) return rc;
   const size_t per_image = mode ? static_cast<size_t>(h0.width) * h0.height * 3 : static_cast<size_t>(h0.width) * h0.height / 2;
   if (out_cap < per_image * n) return fail(GST_ERR_SMALL, "output needs %zu bytes, buffer has %zu", per_image * n, out_cap);
 
-  // one slot per work stream: pinned staging + device input + device output, sized for the
-  // largest page; a slot is reused once the stream that owns it has drained
-  struct Slot {
-    uint8_t *pinned = nullptr, *d_in = nullptr, *d_out = nullptr;
-    size_t cap_in = 0;
-    cudaStream_t stream = nullptr;
-  };
+  std::lock_guard<std::mutex> batch_lock(ctx->host_batch_mutex);
   const uint32_t n_pages = (n + page - 1) / page;
   const uint32_t n_slots = std::min<uint32_t>(kNumWorkStreams, n_pages);
-  std::vector<Slot> slots(n_slots);
-  std::vector<gst_header> hdrs(page);
-  auto cleanup = [&]() {
-    for (auto &s : slots) {
-      if (s.stream) cudaStreamSynchronize(s.stream);
-      if (s.pinned) cudaFreeHost(s.pinned);
-      if (s.d_in) cudaFree(s.d_in);
-      if (s.d_out) cudaFree(s.d_out);
-    }
-  };
-  for (uint32_t pg = 0; pg < n_pages; ++pg) {
-    Slot &s = slots[pg % n_slots];
-    const uint32_t first = pg * page, cnt = std::min(page, n - first);
-    if (!s.stream) s.stream = ctx->streams[1 + pg % n_slots];
-    size_t raw = 0;
-    for (uint32_t i = 0; i < cnt; ++i) raw += lens[first + i];
-    const size_t need = align_up(static_cast<size_t>(cnt) * 32, kQuantum) + raw;  // upper bound on the packed size
-    cudaError_t e = cudaStreamSynchronize(s.stream);  // previous page of this slot is done
-    if (e == cudaSuccess && need > s.cap_in) {
-      if (s.pinned) cudaFreeHost(s.pinned);
-      if (s.d_in) cudaFree(s.d_in);
-      s.pinned = s.d_in = nullptr;
-      s.cap_in = align_up(need + need / 4, 4096);
-      e = cudaHostAlloc(reinterpret_cast<void **>(&s.pinned), s.cap_in, cudaHostAllocDefault);
-      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in);
-    }
-    if (e == cudaSuccess && !s.d_out) e = cudaMalloc(reinterpret_cast<void **>(&s.d_out), per_image * page);
-    if (e != cudaSuccess) {
-      cleanup();
-      return fail(GST_ERR_CUDA, "staging allocation failed: %s", cudaGetErrorString(e));
-    }
-    rc = gst_pack_batch(gst_files + first, lens + first, cnt, s.pinned, s.cap_in, hdrs.data());
-    if (rc) {
-      cleanup();
-      return rc;
-    }
-    const size_t packed = gst_packed_size(hdrs.data(), cnt);
-    e = cudaMemcpyAsync(s.d_in, s.pinned, packed, cudaMemcpyHostToDevice, s.stream);
-    if (e == cudaSuccess) {
-      rc = decode_batch(ctx, hdrs.data(), cnt, s.stream, s.d_in, s.cap_in, s.d_out, mode, Taps{}, nullptr, 0, nullptr);
-      if (rc) {
-        cleanup();
-        return rc;
+  std::vector<int> slot_rc(n_slots, GST_OK);
+  std::vector<std::string> slot_err(n_slots);
+
+  auto worker = [&](uint32_t si) {
+    cudaSetDevice(ctx->device);
+    HostSlot &s = ctx->host_slots[si];
+    cudaStream_t stream = ctx->streams[1 + si];
+    std::vector<gst_header> hdrs(page);
+    auto bail = [&](int code, const char *what, cudaError_t e) {
+      slot_rc[si] = code;
+      slot_err[si] = std::string(what) + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string());
+    };
+    uint32_t turn = 0;
+    for (uint32_t pg = si; pg < n_pages; pg += n_slots, ++turn) {
+      const uint32_t first = pg * page, cnt = std::min(page, n - first);
+      size_t raw = 0;
+      for (uint32_t i = 0; i < cnt; ++i) raw += lens[first + i];
+      const size_t need = align_up(static_cast<size_t>(cnt) * 32, kQuantum) + raw;  // >= packed size
+      const int j = turn & 1;
+      cudaError_t e = cudaSuccess;
+      if (need > s.cap_in) {
+        // grow: drain the stream first, both staging buffers and the device input follow
+        e = cudaStreamSynchronize(stream);
+        for (int k = 0; k < 2; ++k) {
+          if (s.pinned[k]) cudaFreeHost(s.pinned[k]);
+          s.pinned[k] = nullptr;
+        }
+        if (s.d_in) cudaFree(s.d_in);
+        s.d_in = nullptr;
+        s.cap_in = align_up(need + need / 4, 4096);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+          e = cudaHostAlloc(reinterpret_cast<void **>(&s.pinned[k]), s.cap_in, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in);
       }
-      e = cudaMemcpyAsync(out + per_image * first, s.d_out, per_image * cnt, cudaMemcpyDeviceToHost, s.stream);
+      if (e == cudaSuccess && per_image * page > s.cap_out) {
+        e = cudaStreamSynchronize(stream);
+        if (s.d_out) cudaFree(s.d_out);
+        s.d_out = nullptr;
+        s.cap_out = per_image * page;
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_out), s.cap_out);
+      }
+      for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+        if (!s.h2d_done[k]) e = cudaEventCreateWithFlags(&s.h2d_done[k], cudaEventDisableTiming);
+      if (e != cudaSuccess) return bail(GST_ERR_CUDA, "staging allocation failed", e);
+      // the previous upload out of this staging buffer must have left the host
+      e = cudaEventSynchronize(s.h2d_done[j]);
+      if (e != cudaSuccess) return bail(GST_ERR_CUDA, "staging wait failed", e);
+      int prc = gst_pack_batch(gst_files + first, lens + first, cnt, s.pinned[j], s.cap_in, hdrs.data());
+      if (prc) {
+        slot_rc[si] = prc;
+        slot_err[si] = g_err;
+        return;
+      }
+      const size_t packed = gst_packed_size(hdrs.data(), cnt);
+      e = cudaMemcpyAsync(s.d_in, s.pinned[j], packed, cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaEventRecord(s.h2d_done[j], stream);
+      if (e != cudaSuccess) return bail(GST_ERR_CUDA, "upload failed", e);
+      prc = decode_batch(ctx, hdrs.data(), cnt, stream, s.d_in, s.cap_in, s.d_out, mode, Taps{}, nullptr, 0, nullptr);
+      if (prc) {
+        slot_rc[si] = prc;
+        slot_err[si] = g_err;
+        return;
+      }
+      e = cudaMemcpyAsync(out + per_image * first, s.d_out, per_image * cnt, cudaMemcpyDeviceToHost, stream);
+      if (e != cudaSuccess) return bail(GST_ERR_CUDA, "download failed", e);
     }
-    if (e != cudaSuccess) {
-      cleanup();
-      return fail(GST_ERR_CUDA, "page %u failed: %s", pg, cudaGetErrorString(e));
-    }
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) bail(GST_ERR_CUDA, "decode failed", e);
+  };
+
+  if (n_slots == 1) {
+    DeviceGuard guard(ctx->device);
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (uint32_t si = 0; si < n_slots; ++si) pool.emplace_back(worker, si);
+    for (auto &t : pool) t.join();
   }
-  cudaError_t e = cudaSuccess;
-  for (auto &s : slots) {
-    cudaError_t e2 = cudaStreamSynchronize(s.stream);
-    if (e == cudaSuccess) e = e2;
-  }
-  cleanup();
-  if (e != cudaSuccess) return fail(GST_ERR_CUDA, "decode failed: %s", cudaGetErrorString(e));
+  for (uint32_t si = 0; si < n_slots; ++si)
+    if (slot_rc[si]) return fail(slot_rc[si], "%s", slot_err[si].c_str());
   return GST_OK;
 }
 
@@ -625,10 +682,11 @@ int gst_decompress_host(gst_ctx *ctx, const uint8_t *gst, size_t len, int mode, 
 }
 
 // ---- standalone rANS decoder -----------------------------------------------------------
-int gst_normalize_frequencies(const uint32_t *counts, uint32_t n, uint32_t *out) {
+int gst_normalize_frequencies(const uint32_t *counts, uint32_t n, uint32_t target_sum, uint32_t *out) {
   if (!counts || !out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
+  if (target_sum > 0x7FFFFFFFu) return fail(GST_ERR_INVALID, "target sum too large");
   std::vector<uint32_t> h;
-  int rc = normalize_frequencies(counts, n, gst::kTableSize, &h);
+  int rc = normalize_frequencies(counts, n, target_sum ? static_cast<int>(target_sum) : gst::kTableSize, &h);
   if (rc) return rc;
   memcpy(out, h.data(), n * sizeof(uint32_t));
   return GST_OK;
@@ -744,5 +802,40 @@ void gst_ans_destroy(gst_ans_decoder *d) {
 }
 
 int gst_launches_per_batch(void) { return gst::kLaunchesPerBatch; }
+
+int gst_profile_enable(gst_ctx *ctx, int on) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lock(ctx->prof_mutex);
+  ctx->prof_on = on != 0;
+  return GST_OK;
+}
+
+int gst_profile_read(gst_ctx *ctx, double *kernel_ms, uint32_t n_kernels, uint64_t *calls) {
+  if (!ctx || !kernel_ms || !calls) return fail(GST_ERR_INVALID, "null argument");
+  if (n_kernels < static_cast<uint32_t>(gst::kLaunchesPerBatch))
+    return fail(GST_ERR_SMALL, "need room for %d kernel times", gst::kLaunchesPerBatch);
+  DeviceGuard guard(ctx->device);
+  std::vector<cudaEvent_t> evs;
+  {
+    std::lock_guard<std::mutex> lock(ctx->prof_mutex);
+    evs.swap(ctx->prof_events);
+  }
+  for (uint32_t k = 0; k < n_kernels; ++k) kernel_ms[k] = 0.0;
+  const size_t per = gst::kLaunchesPerBatch + 1;
+  *calls = evs.size() / per;
+  cudaError_t err = cudaSuccess;
+  for (size_t c = 0; c < *calls; ++c) {
+    cudaError_t e = cudaEventSynchronize(evs[c * per + per - 1]);
+    for (size_t k = 0; k + 1 < per && e == cudaSuccess; ++k) {
+      float ms = 0.f;
+      e = cudaEventElapsedTime(&ms, evs[c * per + k], evs[c * per + k + 1]);
+      kernel_ms[k] += ms;
+    }
+    if (err == cudaSuccess) err = e;
+  }
+  for (auto ev : evs) cudaEventDestroy(ev);
+  if (err != cudaSuccess) return fail(GST_ERR_CUDA, "profile read failed: %s", cudaGetErrorString(err));
+  return GST_OK;
+}
 
 }  // extern "C"

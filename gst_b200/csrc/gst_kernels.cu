@@ -676,13 +676,17 @@ static cudaError_t ensure_attrs() {
 }
 
 cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,
-                                cudaStream_t s) {
+                                cudaStream_t s, cudaEvent_t *marks) {
   if (p.n_images == 0) return cudaSuccess;
   cudaError_t e = ensure_attrs();
   if (e != cudaSuccess) return e;
+  int mark = 0;
+  auto stamp = [&]() { return marks ? cudaEventRecord(marks[mark++], s) : cudaSuccess; };
+  if ((e = stamp()) != cudaSuccess) return e;
   // stage 1: 4 tables per image, straight from the freq region of the compressed buffer
   e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s);
   if (e != cudaSuccess) return e;
+  if ((e = stamp()) != cudaSuccess) return e;
   // palette + index streams
   const uint32_t max_pal_groups = max_palette_bytes / kGroupSyms;
   const uint32_t pal_ctas = (max_pal_groups + kSideWarps - 1) / kSideWarps;
@@ -690,15 +694,19 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   side_streams_kernel<<<p.n_images * (pal_ctas + idx_ctas), kSideWarps * 32, kSideSmem, s>>>(p, pal_ctas, idx_ctas);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if ((e = stamp()) != cudaSuccess) return e;
   index_carry_kernel<<<p.n_images, 32, 0, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if ((e = stamp()) != cudaSuccess) return e;
   const uint32_t grid = p.n_images * p.groups_per_plane;
   if (rgb_mode)
     fused_planes_kernel<1><<<grid, kFusedWarps * 32, kFusedSmem, s>>>(p);
   else
     fused_planes_kernel<0><<<grid, kFusedWarps * 32, kFusedSmem, s>>>(p);
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return stamp();
 }
 
 cudaError_t launch_ans_decode_plain(const uint32_t *table, const uint8_t *data, uint64_t data_bytes,

@@ -60,8 +60,9 @@ struct BatchParams {
 cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,
                                 cudaStream_t s);
 // max_palette_bytes = max over the batch of GenTCHeader::palette_bytes (sizes the grid)
+// marks: NULL, or kLaunchesPerBatch + 1 events recorded around every kernel (profiling)
 cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,
-                                cudaStream_t s);
+                                cudaStream_t s, cudaEvent_t *marks = nullptr);
 cudaError_t launch_ans_decode_plain(const uint32_t *table, const uint8_t *data,
                                     uint64_t data_bytes, uint32_t n_groups, uint32_t n_lanes,
                                     uint8_t *out, cudaStream_t s);

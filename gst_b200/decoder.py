@@ -118,11 +118,12 @@ def pack_batch(files, out=None):
     return out[:size], [GenTCHeader.from_c(h) for h in hdrs]
 
 
-def normalize_frequencies(counts):
-    """ans::ocl::NormalizeFrequencies (ans/ans_ocl_encode.cpp:6-8)."""
+def normalize_frequencies(counts, target_sum=kANSTableSize):
+    """ans::ocl::NormalizeFrequencies (ans/ans_ocl_encode.cpp:6-8) =
+    ans::GenerateHistogram(counts, 2048) (ans/histogram.cpp:41-123)."""
     c = np.ascontiguousarray(counts, dtype=np.uint32)
     out = np.zeros_like(c)
-    check(lib().gst_normalize_frequencies(c.ctypes.data_as(C.POINTER(C.c_uint32)), c.size,
+    check(lib().gst_normalize_frequencies(c.ctypes.data_as(C.POINTER(C.c_uint32)), c.size, int(target_sum),
                                           out.ctypes.data_as(C.POINTER(C.c_uint32))))
     return out
 
@@ -263,6 +264,20 @@ class Decoder:
         check(lib().gst_memset_async(self.ctx, s, dbuf.ptr, int(value), dbuf.nbytes))
         if stream is None:
             self.sync(s)
+
+    # -- profiling -----------------------------------------------------------------------
+    KERNEL_NAMES = ("build_tables", "side_streams", "index_carry", "fused_planes")
+
+    def profile(self, on=True):
+        check(lib().gst_profile_enable(self.ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """-> ({kernel name: total ms}, number of decode calls covered)."""
+        n = lib().gst_launches_per_batch()
+        ms = (C.c_double * n)()
+        calls = C.c_uint64()
+        check(lib().gst_profile_read(self.ctx, ms, n, C.byref(calls)))
+        return dict(zip(self.KERNEL_NAMES, list(ms))), int(calls.value)
 
     # -- scratch -------------------------------------------------------------------------
     def PreallocateDecompressor(self, req_sz):

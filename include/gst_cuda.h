@@ -153,7 +153,10 @@ int gst_load_dxt_batch_tapped(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, 
  *   is the final encoder state of lane l, data[g]/data_len[g] the group's renorm bytes as
  *   written by the encoder.  out receives groups*lanes*256 symbols, out[(g*lanes+l)*256+i]. */
 typedef struct gst_ans_decoder gst_ans_decoder;
-int gst_normalize_frequencies(const uint32_t *counts, uint32_t n, uint32_t *out);
+/* ans::GenerateHistogram(counts, target_sum) (ans/histogram.cpp:41-123); target_sum 0 means
+ * 2048 = ans::ocl::NormalizeFrequencies.  Host only. */
+int gst_normalize_frequencies(const uint32_t *counts, uint32_t n, uint32_t target_sum,
+                              uint32_t *out);
 int gst_ans_create(gst_ctx *ctx, const uint32_t *F, uint32_t n, uint32_t lanes,
                    gst_ans_decoder **out);
 int gst_ans_rebuild(gst_ans_decoder *d, const uint32_t *F, uint32_t n);
@@ -168,8 +171,17 @@ void gst_ans_destroy(gst_ans_decoder *d);
 int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t n_tables,
                      void *tables_dev);
 
-/* number of kernel launches one gst_load_*_batch call enqueues */
+/* number of kernel launches one gst_load_*_batch call enqueues, in launch order:
+ * build_tables, side_streams (palette + index rANS), index_carry, fused_planes */
 int gst_launches_per_batch(void);
+
+/* Per-kernel device timing for the benchmark's roofline line (no reference equivalent; the
+ * reference only has wall-clock prints, demo/photos_sf.cpp:851,892-893).  While enabled,
+ * every gst_load_*_batch call records CUDA events on its stream around each of its kernels.
+ * gst_profile_read waits for the recorded calls, adds the elapsed milliseconds of kernel k
+ * over all calls since the last read into kernel_ms[k] and returns the number of calls. */
+int gst_profile_enable(gst_ctx *ctx, int on);
+int gst_profile_read(gst_ctx *ctx, double *kernel_ms, uint32_t n_kernels, uint64_t *calls);
 
 #ifdef __cplusplus
 }

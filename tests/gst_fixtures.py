@@ -164,21 +164,23 @@ def encode_image(width, height, seed, noise_only=False):
 
 
 def encode_images(width, height, seeds, workers=None):
-    """encode_image for many seeds on a process pool (the reference encoder is ~3 s per
-    2048x2048 image per core)."""
+    """encode_image for many seeds, missing ones on parallel worker processes (the reference
+    encoder is ~3 s per 2048x2048 image per core and narrates through a global std::cout, so
+    the workers are separate processes, not threads)."""
     missing = [s for s in seeds if not os.path.exists(os.path.join(CACHE_DIR, f"synth_{width}x{height}_s{s}.gst"))]
     if len(missing) > 1:
-        import concurrent.futures as cf
-        import multiprocessing as mp
+        import sys
         workers = workers or min(len(missing), os.cpu_count() or 1)
-        with cf.ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
-            list(ex.map(_encode_one, [(width, height, s) for s in missing]))
+        procs = []
+        for k in range(workers):
+            part = missing[k::workers]
+            if part:
+                procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--encode", str(width),
+                                               str(height)] + [str(s) for s in part]))
+        for pr in procs:
+            if pr.wait() != 0:
+                raise RuntimeError("fixture encoder worker failed")
     return [encode_image(width, height, s) for s in seeds]
-
-
-def _encode_one(args):
-    encode_image(*args)
-    return 0
 
 
 def golden_test1():
@@ -323,3 +325,10 @@ def random_gst(width, height, seed, palette_entries=2048, plane_mode="laplace"):
 
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 4 and sys.argv[1] == "--encode":
+        for seed in sys.argv[4:]:
+            encode_image(int(sys.argv[2]), int(sys.argv[3]), int(seed))

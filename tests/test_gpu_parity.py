@@ -35,3 +35,137 @@ def test_stages_golden_streams(decoder):
         gst = np.fromfile(f"{fx.GOLDEN_DIR}/{name}.gst", dtype=np.uint8)
         res = decoder.decode_tapped([gst])
         _check_stages(res, 0, gst)
+
+
+def test_batch_mixed_streams_all_stages(decoder):
+    """LoadCompressedDXTs with several different 512x512 streams in one call (photos_sf
+    layout): every stage of every image against the oracle."""
+    files = [fx.golden_test1()[0], np.fromfile(f"{fx.GOLDEN_DIR}/synth512_s7.gst", dtype=np.uint8)]
+    files += [fx.encode_image(512, 512, 10000 + i)[0] for i in range(3)]
+    files += [fx.random_gst(512, 512, seed=21, palette_entries=5000)]  # palette_bytes = 24576
+    res = decoder.decode_tapped(files)
+    assert len({h.palette_bytes for h in res["hdrs"]}) > 1
+    for i, f in enumerate(files):
+        _check_stages(res, i, f)
+
+
+@pytest.mark.parametrize("mode", ["uniform", "extreme", "laplace"])
+def test_adversarial_symbol_planes(decoder, mode):
+    """Symbol planes no encoder would emit (uniform / extreme bytes): exercises the int16
+    work-tile bound of the wavelet, the (char) truncation and the unmasked 565 pack."""
+    gst = fx.random_gst(512, 256, seed=3 + len(mode), palette_entries=2048, plane_mode=mode)
+    res = decoder.decode_tapped([gst])
+    _check_stages(res, 0, gst)
+
+
+@pytest.mark.parametrize("wh", [(256, 512), (1024, 128), (128, 1024), (1920, 1024), (640, 1024)])
+def test_geometries(decoder, wh, ref_lib):
+    """Tile-major planes vs raster indices on non-square / non-power-of-two block grids
+    (tiles_x = 2, 8, 1, 15, 5)."""
+    w, h = wh
+    if (w, h) == (1920, 1024):
+        gst, golden = fx.encode_image(w, h, 40000)
+    else:
+        gst, golden = fx.random_gst(w, h, seed=w + h, palette_entries=1500), None
+    res = decoder.decode_tapped([gst, gst])
+    _check_stages(res, 0, gst)
+    _check_stages(res, 1, gst)
+    if golden is not None:
+        assert np.array_equal(res["dxt"][: golden.size], golden)
+
+
+def test_rgb_output_mode(decoder):
+    """LoadRGB / assemble_rgb (codec/assemble.cl:83-129) against the oracle, single and batched."""
+    g1 = fx.golden_test1()[0]
+    g2 = fx.random_gst(512, 512, seed=9, palette_entries=700, plane_mode="uniform")
+    for g in (g1, g2):
+        want = fx.oracle_decode(g, mode=1, taps=False)["out"]
+        assert np.array_equal(decoder.DecompressDXT(g, mode=1), want)
+    out = decoder.DecompressDXTs([g1, g2, g1], page=2, mode=1)
+    per = 512 * 512 * 3
+    assert np.array_equal(out[per:2 * per], fx.oracle_decode(g2, mode=1, taps=False)["out"])
+    assert np.array_equal(out[2 * per:], out[:per])
+
+
+def test_large_single_texture(decoder):
+    """configs[2]: one 4096x4096 texture (128 rANS groups per plane)."""
+    gst, golden = fx.encode_image(4096, 4096, 20000)
+    out = decoder.DecompressDXT(gst)
+    assert np.array_equal(out, golden)
+    res = decoder.decode_tapped([gst])
+    _check_stages(res, 0, gst)
+
+
+def test_big_batch_tiled(decoder):
+    """configs[3] shape at a size that runs in seconds: 96 x 2048x2048 tiled from 4 distinct
+    streams; every output image must equal the encoder's PhysicalBlocks() of its source, and
+    equal inputs must give equal outputs wherever they sit in the batch."""
+    srcs = [fx.encode_image(2048, 2048, 30000 + i) for i in range(4)]
+    order = [(7 * i) % 4 for i in range(96)]
+    out = decoder.DecompressDXTs([srcs[j][0] for j in order], page=96)
+    per = 2048 * 2048 // 2
+    for pos, j in enumerate(order):
+        assert np.array_equal(out[pos * per:(pos + 1) * per], srcs[j][1]), f"image {pos}"
+    want = fx.oracle_decode(srcs[0][0], taps=False)["out"]
+    assert np.array_equal(out[:per], want)
+    # the same batch in pages of 16 over the four work streams
+    out2 = decoder.DecompressDXTs([srcs[j][0] for j in order], page=16)
+    assert np.array_equal(out, out2)
+
+
+def test_async_api_events_and_scratch_arena(decoder):
+    """LoadCompressedDXT(s) on caller-owned device buffers and a work queue, ordered by events,
+    with PreallocateDecompressor (bump arena, never reset: codec/decoder.cpp:74-82)."""
+    import gst_b200
+    files = [fx.encode_image(512, 512, 10000 + i)[0] for i in range(4)]
+    goldens = [fx.encode_image(512, 512, 10000 + i)[1] for i in range(4)]
+    packed, hdrs = gst_b200.pack_batch(files)
+    need = sum(gst_b200.required_scratch_mem(h) for h in hdrs)
+    decoder.PreallocateDecompressor(2 * need)
+    try:
+        q_up, q = decoder.GetNextQueue(), decoder.GetNextQueue()
+        assert q_up != q
+        d_cmp, d_out = decoder.malloc(packed.size), decoder.malloc(4 * 131072)
+        pin = decoder.pinned(packed.size)
+        pin.array[:] = packed
+        decoder.upload(d_cmp, pin, stream=q_up)
+        copied = decoder.record(q_up)
+        for _ in range(2):  # two calls fit the arena
+            done = decoder.LoadCompressedDXTs(hdrs, q, d_cmp, d_out, init=[copied])
+            done.wait()
+            out = decoder.download(d_out)
+            assert np.array_equal(out, np.concatenate(goldens))
+            done.destroy()
+        with pytest.raises(gst_b200.GstError) as e:  # the arena is never reset
+            for _ in range(64):
+                decoder.LoadCompressedDXTs(hdrs, q, d_cmp, d_out, want_event=False)
+        assert e.value.code == -4
+        decoder.sync()
+    finally:
+        decoder.FreeDecompressor()
+    # without an arena: single-image entry point
+    one, h1 = gst_b200.pack_batch(files[:1])
+    d1 = decoder.malloc(one.size)
+    decoder.upload(d1, one)
+    ev = decoder.LoadCompressedDXT(h1[0], decoder.GetDefaultCommandQueue(), d1, d_out)
+    ev.wait()
+    assert np.array_equal(decoder.download(d_out, 131072), goldens[0])
+
+
+def test_errors_are_reported_not_swallowed(decoder):
+    import gst_b200
+    files = [fx.golden_test1()[0]]
+    packed, hdrs = gst_b200.pack_batch(files)
+    d_cmp, d_out = decoder.malloc(packed.size), decoder.malloc(131072)
+    decoder.upload(d_cmp, packed)
+    with pytest.raises(gst_b200.GstError):  # buffer shorter than the headers say
+        decoder.LoadCompressedDXTs(hdrs, decoder.GetDefaultCommandQueue(), d_cmp, d_out, cmp_bytes=packed.size - 8)
+    with pytest.raises(gst_b200.GstError):
+        decoder.DecompressDXT(files[0][:5000])
+
+
+def test_deterministic(decoder):
+    gst = fx.encode_image(2048, 2048, 30001)[0]
+    a = decoder.DecompressDXTs([gst] * 8, page=8)
+    b = decoder.DecompressDXTs([gst] * 8, page=3)
+    assert np.array_equal(a, b)
