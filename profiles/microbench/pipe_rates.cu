@@ -1,0 +1,100 @@
+// Micro-benchmark: sustained throughput of the integer instructions the decode kernels lean on,
+// per SM per clock on B200 (sm_100a).  Each kernel runs 8 independent dependency chains per
+// thread, 1024 threads per block, 2 blocks per SM, so the issue ports -- not latency -- bound it.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_rates pipe_rates.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ITERS 4096
+#define ILP 8
+
+#define BENCH_KERNEL(NAME, BODY)                                                    \
+  __global__ void __launch_bounds__(1024) NAME(uint32_t *out, uint32_t seed) {      \
+    uint32_t v[ILP];                                                                \
+    uint32_t k = seed + threadIdx.x, c = seed * 3 + 1;                              \
+    _Pragma("unroll") for (int j = 0; j < ILP; ++j) v[j] = k * (j + 1) + seed;      \
+    for (int i = 0; i < ITERS; ++i) {                                               \
+      _Pragma("unroll") for (int j = 0; j < ILP; ++j) { BODY }                      \
+    }                                                                               \
+    uint32_t s = 0;                                                                 \
+    _Pragma("unroll") for (int j = 0; j < ILP; ++j) s ^= v[j];                      \
+    if (s == 0x12345678u) out[threadIdx.x] = s + k + c;                             \
+  }
+
+BENCH_KERNEL(k_lop3, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_shf, asm volatile("shr.u32 %0, %0, 1;" : "+r"(v[j])); asm volatile("shl.b32 %0, %0, 1;" : "+r"(v[j]));)
+BENCH_KERNEL(k_shr, asm volatile("shf.r.clamp.b32 %0, %0, %1, 3;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_iadd, asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_imad, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_imadhi, asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_prmt, asm volatile("prmt.b32 %0, %0, %1, 0x2104;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_popc, asm volatile("popc.b32 %0, %0;" : "+r"(v[j])); v[j] += k;)
+BENCH_KERNEL(k_setp, { uint32_t t; asm volatile("{ .reg .pred p; setp.lt.u32 p, %1, %2; selp.u32 %0, %1, %2, p; }" : "=r"(t) : "r"(v[j]), "r"(c)); v[j] = t + 1; })
+BENCH_KERNEL(k_vote, { uint32_t t; asm volatile("{ .reg .pred p; setp.lt.u32 p, %1, %2; vote.sync.ballot.b32 %0, p, 0xffffffff; }" : "=r"(t) : "r"(v[j]), "r"(c)); v[j] += t; })
+BENCH_KERNEL(k_shfl, asm volatile("shfl.sync.idx.b32 %0, %0, 0, 0x1f, 0xffffffff;" : "+r"(v[j])); v[j] += k;)
+BENCH_KERNEL(k_mix_lop_imad, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_mix_lop_imadhi, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_lop_shf, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("shf.r.clamp.b32 %0, %0, %1, 3;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_lop_popc, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("popc.b32 %0, %0;" : "+r"(v[j]));)
+BENCH_KERNEL(k_ffma, { float f = __uint_as_float(v[j]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); v[j] = __float_as_uint(f); })
+BENCH_KERNEL(k_mix_lop_ffma, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); { float f = __uint_as_float(v[j]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); v[j] = __float_as_uint(f); })
+BENCH_KERNEL(k_hadd2, asm volatile("add.f16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_dp4a, asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_vabsdiff, asm volatile("vadd2.s32.s32.s32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
+
+__global__ void __launch_bounds__(1024) k_lds(uint32_t *out, uint32_t seed) {
+  __shared__ uint32_t tab[2048];
+  for (int i = threadIdx.x; i < 2048; i += 1024) tab[i] = (i * 2654435761u + seed) & 2047;
+  __syncthreads();
+  uint32_t v[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) v[j] = (threadIdx.x * 37 + j * 101 + seed) & 2047;
+  for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) v[j] = tab[v[j]];
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) s ^= v[j];
+  if (s == 0x12345678u) out[threadIdx.x] = s;
+}
+
+typedef void (*kern_t)(uint32_t *, uint32_t);
+
+int main() {
+  uint32_t *out;
+  cudaMalloc(&out, 4096 * 4);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, 0);
+  const int sms = prop.multiProcessorCount;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+  struct { const char *name; kern_t k; int ops; } ks[] = {
+      {"LOP3", k_lop3, 1}, {"SHR+SHL (2 ops)", k_shf, 2}, {"SHF.R funnel", k_shr, 1}, {"IADD", k_iadd, 1},
+      {"IMAD.lo", k_imad, 1}, {"IMAD.HI (mul.hi)", k_imadhi, 1}, {"PRMT", k_prmt, 1}, {"POPC (+IADD)", k_popc, 2},
+      {"SETP+SELP (+IADD)", k_setp, 3}, {"SETP+VOTE.ballot (+IADD)", k_vote, 3}, {"SHFL.idx (+IADD)", k_shfl, 2},
+      {"LOP3+IMAD alternating", k_mix_lop_imad, 2}, {"LOP3+IMAD.HI alternating", k_mix_lop_imadhi, 2},
+      {"LOP3+SHF alternating", k_mix_lop_shf, 2}, {"LOP3+POPC alternating", k_mix_lop_popc, 2}, {"FFMA", k_ffma, 1},
+      {"LOP3+FFMA alternating", k_mix_lop_ffma, 2}, {"HADD2 (add.f16x2)", k_hadd2, 1}, {"DP4A", k_dp4a, 1},
+      {"vadd2 (SIMD video, emulated?)", k_vabsdiff, 1}, {"LDS random 2048-entry gather", k_lds, 1}};
+  printf("device %s, %d SMs, clock attr %d kHz\n", prop.name, sms, khz);
+  printf("%-34s %12s %16s\n", "instruction", "ms", "thread-ops/clk/SM");
+  for (auto &e : ks) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    e.k<<<sms * 2, 1024>>>(out, 1);
+    cudaDeviceSynchronize();
+    cudaEventRecord(a);
+    e.k<<<sms * 2, 1024>>>(out, 1);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    double ops = double(sms) * 2 * 1024 * ITERS * ILP * e.ops;
+    double per_clk_sm = ops / (ms * 1e-3) / (double(khz) * 1e3) / sms;
+    printf("%-34s %12.4f %16.1f\n", e.name, ms, per_clk_sm);
+  }
+  return 0;
+}

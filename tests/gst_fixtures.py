@@ -144,21 +144,44 @@ def encode_rgb(img):
     return gst[: n.value].copy(), dxt
 
 
+class GoldenSha(str):
+    """sha256 of a golden DXT1 image too large to keep on disk (see encode_image)."""
+
+
+BIG_PIXELS = 1024 * 1024  # goldens above this are cached as a sha256, not as 0.5 B/texel of blocks
+
+
+def matches_golden(out, golden):
+    """out == the encoder's PhysicalBlocks(), given either the blocks or their GoldenSha."""
+    if isinstance(golden, GoldenSha):
+        return sha(out) == golden
+    return bool(np.array_equal(out, golden))
+
+
 def encode_image(width, height, seed, noise_only=False):
-    """Seeded synthetic image through the reference encoder, cached on disk."""
+    """Seeded synthetic image through the reference encoder, cached on disk.  Returns
+    (.gst bytes, golden) where golden is the encoder's PhysicalBlocks() as a uint8 array, or,
+    for images above 1 Mpixel, its GoldenSha (keeps the cache that travels to the GPU box small)."""
     os.makedirs(CACHE_DIR, exist_ok=True)
     tag = f"{'noise' if noise_only else 'synth'}_{width}x{height}_s{seed}"
-    pg, pd = os.path.join(CACHE_DIR, tag + ".gst"), os.path.join(CACHE_DIR, tag + ".dxt")
-    if os.path.exists(pg) and os.path.exists(pd):
-        return np.fromfile(pg, dtype=np.uint8), np.fromfile(pd, dtype=np.uint8)
+    pg, pd, ps = (os.path.join(CACHE_DIR, tag + ext) for ext in (".gst", ".dxt", ".sha"))
+    big = width * height > BIG_PIXELS
+    if os.path.exists(pg) and os.path.exists(ps if big else pd):
+        gst = np.fromfile(pg, dtype=np.uint8)
+        return gst, (GoldenSha(open(ps).read().strip()) if big else np.fromfile(pd, dtype=np.uint8))
     if noise_only:
         img = np.random.default_rng(seed).integers(0, 256, size=(height, width, 3), dtype=np.uint8)
     else:
         img = synth_image(width, height, seed)
     gst, dxt = encode_rgb(img)
     gst.tofile(pg + ".tmp")
-    dxt.tofile(pd + ".tmp")
     os.replace(pg + ".tmp", pg)
+    if big:
+        with open(ps + ".tmp", "w") as f:
+            f.write(sha(dxt))
+        os.replace(ps + ".tmp", ps)
+        return gst, GoldenSha(sha(dxt))
+    dxt.tofile(pd + ".tmp")
     os.replace(pd + ".tmp", pd)
     return gst, dxt
 
@@ -167,7 +190,9 @@ def encode_images(width, height, seeds, workers=None):
     """encode_image for many seeds, missing ones on parallel worker processes (the reference
     encoder is ~3 s per 2048x2048 image per core and narrates through a global std::cout, so
     the workers are separate processes, not threads)."""
-    missing = [s for s in seeds if not os.path.exists(os.path.join(CACHE_DIR, f"synth_{width}x{height}_s{s}.gst"))]
+    ext = ".sha" if width * height > BIG_PIXELS else ".dxt"
+    missing = [s for s in seeds if not (os.path.exists(os.path.join(CACHE_DIR, f"synth_{width}x{height}_s{s}.gst")) and
+                                        os.path.exists(os.path.join(CACHE_DIR, f"synth_{width}x{height}_s{s}{ext}")))]
     if len(missing) > 1:
         import sys
         workers = workers or min(len(missing), os.cpu_count() or 1)

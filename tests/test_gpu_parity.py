@@ -71,7 +71,7 @@ def test_geometries(decoder, wh, ref_lib):
     _check_stages(res, 0, gst)
     _check_stages(res, 1, gst)
     if golden is not None:
-        assert np.array_equal(res["dxt"][: golden.size], golden)
+        assert fx.matches_golden(res["dxt"][: 8 * res["hdrs"][0].num_blocks], golden)
 
 
 def test_rgb_output_mode(decoder):
@@ -91,7 +91,7 @@ def test_large_single_texture(decoder):
     """configs[2]: one 4096x4096 texture (128 rANS groups per plane)."""
     gst, golden = fx.encode_image(4096, 4096, 20000)
     out = decoder.DecompressDXT(gst)
-    assert np.array_equal(out, golden)
+    assert fx.matches_golden(out, golden)
     res = decoder.decode_tapped([gst])
     _check_stages(res, 0, gst)
 
@@ -105,7 +105,7 @@ def test_big_batch_tiled(decoder):
     out = decoder.DecompressDXTs([srcs[j][0] for j in order], page=96)
     per = 2048 * 2048 // 2
     for pos, j in enumerate(order):
-        assert np.array_equal(out[pos * per:(pos + 1) * per], srcs[j][1]), f"image {pos}"
+        assert fx.matches_golden(out[pos * per:(pos + 1) * per], srcs[j][1]), f"image {pos}"
     want = fx.oracle_decode(srcs[0][0], taps=False)["out"]
     assert np.array_equal(out[:per], want)
     # the same batch in pages of 16 over the four work streams
