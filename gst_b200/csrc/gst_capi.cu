@@ -112,7 +112,8 @@ struct BatchLayout {
   uint32_t n_blocks = 0, groups_per_plane = 0, max_palette = 0;
   size_t off_region = 0, payload_bytes = 0, palette_total = 0, total_cmp = 0;
   // scratch carve-up
-  size_t tables_off = 0, palette_off = 0, local_off = 0, total_off = 0, carry_off = 0, scratch_bytes = 0;
+  size_t tables_off = 0, palette_off = 0, idx_off = 0, total_off = 0, run_off = 0, scratch_bytes = 0;
+  bool idx16 = true;
 };
 
 int layout_batch(const gst_header *hdrs, uint32_t n, BatchLayout *L) {
@@ -145,9 +146,11 @@ int layout_batch(const gst_header *hdrs, uint32_t n, BatchLayout *L) {
   size_t off = 0;
   L->tables_off = off;  off += align_up(static_cast<size_t>(n) * 4 * gst::kTableSize * 4, kQuantum);
   L->palette_off = off; off += align_up(std::max<size_t>(L->palette_total, 16), kQuantum);
-  L->local_off = off;   off += align_up(static_cast<size_t>(n) * N * 4, kQuantum);
+  // palette indices < 2^16 everywhere -> the per-block index suffix sums are kept as u16
+  L->idx16 = max_pal / 4 <= 65536u;
+  L->idx_off = off;     off += align_up(static_cast<size_t>(n) * N * (L->idx16 ? 2 : 4), kQuantum);
   L->total_off = off;   off += align_up(static_cast<size_t>(n) * L->groups_per_plane * 4, kQuantum);
-  L->carry_off = off;   off += align_up(static_cast<size_t>(n) * L->groups_per_plane * 4, kQuantum);
+  L->run_off = off;     off += align_up(static_cast<size_t>(n) * (N / gst::kSymsPerLane) * 4, kQuantum);
   L->scratch_bytes = off;
   return GST_OK;
 }
@@ -198,9 +201,10 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.tables = reinterpret_cast<uint32_t *>(scratch + L.tables_off);
   p.palette = scratch + L.palette_off;
   p.palette_cap = L.palette_total;
-  p.idx_local = reinterpret_cast<int32_t *>(scratch + L.local_off);
+  p.idx_s = scratch + L.idx_off;
+  p.idx16 = L.idx16 ? 1u : 0u;
   p.idx_total = reinterpret_cast<int32_t *>(scratch + L.total_off);
-  p.idx_carry = reinterpret_cast<int32_t *>(scratch + L.carry_off);
+  p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
   p.tap_symbols = static_cast<uint8_t *>(taps.symbols);
   p.tap_planes = static_cast<int8_t *>(taps.planes);

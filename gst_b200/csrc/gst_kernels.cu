@@ -22,9 +22,50 @@ namespace gst {
 namespace {
 
 // ---------------------------------------------------------------------------------------
-// small PTX helpers
+// small PTX helpers.  Shared memory is addressed by its 32-bit shared-window address so the
+// hot loops spend no instructions on generic-address arithmetic.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t a) {
+  int v;
+  asm volatile("{ .reg .s16 t; ld.shared.s16 t, [%1]; cvt.s32.s16 %0, t; }" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+  asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u8 [%0], t; }" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+  asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
@@ -37,10 +78,30 @@ __device__ __forceinline__ uint32_t lanemask_gt() {
   asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
   return m;
 }
-__device__ __forceinline__ void st_global_cs_v4(void *p, uint4 v) {
-  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(v.x), "r"(v.y),
-               "r"(v.z), "r"(v.w)
-               : "memory");
+__device__ __forceinline__ void st_global_cs_v4(void *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// prmt.b32 in its default mode: a selector nibble with bit 3 set replicates the SIGN of the
+// selected byte (the __byte_perm intrinsic only documents the low three bits, so use PTX).
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+  return d;
+}
+// signed byte j of w as int; byte pair (j, j+1) as a packed int16x2 word
+template <int J>
+__device__ __forceinline__ int sext_byte(uint32_t w) {
+  return static_cast<int>(prmt<((8 | J) << 12) | ((8 | J) << 8) | ((8 | J) << 4) | J>(w, 0u));
+}
+template <int J>
+__device__ __forceinline__ uint32_t sext_byte_pair(uint32_t w) {
+  return prmt<((8 | (J + 1)) << 12) | ((J + 1) << 8) | ((8 | J) << 4) | J>(w, 0u);
+}
+__device__ __forceinline__ int lo16(uint32_t w) { return static_cast<int>(prmt<0x9910>(w, 0u)); }
+__device__ __forceinline__ int hi16(uint32_t w) { return static_cast<int>(w) >> 16; }
+__device__ __forceinline__ uint32_t pack16(int a, int b) {
+  return __byte_perm(static_cast<uint32_t>(a), static_cast<uint32_t>(b), 0x5410);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -50,11 +111,19 @@ __device__ __forceinline__ void st_global_cs_v4(void *p, uint4 v) {
 // a group ends with its n_lanes 32-bit states, preceded by the shared 16-bit renorm words,
 // which are consumed backwards, higher lanes first (ans/ans_decode.cl:30-32,51-65).
 //
-// The renorm words are staged through a per-warp shared-memory ring filled with cp.async in
-// 256-byte, 256-byte-aligned chunks (group ranges are only 4-byte aligned, so windows are
-// aligned down in absolute address space).  A checkpoint every 4 symbols tops the ring up;
-// 4 symbols consume at most 4*32*2 = 256 B, and a refill is issued whenever fewer than 512 B
-// are staged, so a chunk is always complete one checkpoint before its first byte is needed.
+// The renorm words are staged through a per-warp, 1 KiB-aligned shared-memory ring filled with
+// cp.async in 256-byte, 256-byte-aligned chunks (group ranges are only 4-byte aligned, so the
+// windows are aligned down in absolute address space and the ring is indexed by the low
+// address bits).  A checkpoint every 4 symbols tops the ring up; 4 symbols consume at most
+// 4*32*2 = 256 B and a refill is issued whenever fewer than 512 B are staged, so a chunk is
+// always complete one checkpoint before its first byte is needed.
+//
+// Per symbol and lane (ans/ans_decode.cl:38-65):
+//   e = table[state & 2047];  state = (state >> 11) * e.freq + e.bias          (bias = slot - cum)
+//   lanes whose state fell below L = 2^15 take the next 16-bit word, higher lanes first:
+//   word index = next - 1 - popc(ballot & lanes_above_me);  next -= popc(ballot)
+// The word load is unconditional (every lane's address lies inside the staged 64 bytes), only
+// the state update is predicated.
 constexpr int kRing = 1024;
 constexpr int kChunk = 256;
 constexpr int kRunStride = 264;                    // one lane's 256 symbols + 8 B pad (66 words:
@@ -63,16 +132,13 @@ constexpr int kStagePlane = kLanes * kRunStride;   // 8448 B: one decoded group
 
 // emit(m, lo, hi): called 32 times; the 8 symbols at positions q0 = 248 - 8m .. q0 + 7 of this
 // lane's 256-symbol run, little-endian packed (lo = q0..q0+3, hi = q0+4..q0+7).
-template <class Emit>
-__device__ __forceinline__ void rans_decode_group(const uint32_t *__restrict__ tab,
-                                                  const uint8_t *__restrict__ stream,
-                                                  uint32_t group, uint32_t n_lanes, uint8_t *ring,
-                                                  const uint8_t *buf_lo, const uint8_t *buf_hi,
-                                                  Emit emit) {
+template <bool FULL, class Emit>
+__device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t *__restrict__ stream,
+                                                  uint32_t group, uint32_t n_lanes, uint32_t ring_s,
+                                                  const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gt = lanemask_gt();
-  const bool active = lane < n_lanes;
-  const uint32_t ring_s = smem_u32(ring);
+  const bool active = FULL || lane < n_lanes;
 
   // ans/ans_decode.cl:30.  Clamp so a malformed offset can never leave [buf_lo, buf_hi).
   const uint32_t end = __ldg(reinterpret_cast<const uint32_t *>(stream) + group) & ~3u;
@@ -99,17 +165,17 @@ __device__ __forceinline__ void rans_decode_group(const uint32_t *__restrict__ t
       cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
   }
 
-  uint32_t cur = static_cast<uint32_t>(a_pos);  // low address bits; next word is at cur - 2
+  uint32_t cur2 = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
 
 #pragma unroll 1
   for (int m = 0; m < 32; ++m) {
     uint32_t acc[2] = {0u, 0u};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      // checkpoint
+      // checkpoint: everything issued so far has landed; top up when < 512 B are staged
       cp_async_wait_all();
       __syncwarp();
-      if (cur - static_cast<uint32_t>(lo) < 512u) {
+      if (cur2 - static_cast<uint32_t>(lo) < 510u) {
         lo -= kChunk;
         const uintptr_t a = lo + 16 * lane;
         if (lane < 16 && a >= lo16 && a + 16 <= hi16)
@@ -117,19 +183,17 @@ __device__ __forceinline__ void rans_decode_group(const uint32_t *__restrict__ t
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        // ans/ans_decode.cl:38-41 with freq / (slot - cum_freq) / symbol packed in one word
-        const uint32_t e = tab[state & (kTableSize - 1)];
+        uint32_t slot_a;  // tab_s + 4 * (state & 2047): one LOP3 + one IMAD
+        asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(state & (kTableSize - 1)), "r"(tab_s));
+        const uint32_t e = lds32(slot_a);
         state = (state >> kTableLog) * ((e >> 8) & 0xFFFu) + (e >> 20);
-        // ans/ans_decode.cl:44-57: lanes below L pull one 16-bit word, higher lanes first
-        const bool need = active && state < kRansL;
+        const bool need = FULL ? (state < kRansL) : (active && state < kRansL);
         const uint32_t mask = __ballot_sync(0xffffffffu, need);
-        if (need) {
-          const uint32_t a = cur - 2u - 2u * __popc(mask & gt);
-          const uint32_t w = *reinterpret_cast<const uint16_t *>(ring + (a & (kRing - 1)));
-          state = (state << 16) | w;
-        }
-        cur -= 2u * __popc(mask);  // ans/ans_decode.cl:65
-        acc[1 - h] = __byte_perm(acc[1 - h], e, 0x2104);  // acc = acc << 8 | symbol
+        const uint32_t a = cur2 - 2u * __popc(mask & gt);
+        const uint32_t w = lds_u16(ring_s | (a & (kRing - 1)));
+        if (need) state = __byte_perm(w, state, 0x5410);  // state << 16 | w
+        cur2 -= 2u * __popc(mask);                        // ans/ans_decode.cl:65
+        acc[1 - h] = __byte_perm(acc[1 - h], e, 0x2104);  // acc << 8 | symbol
       }
     }
     emit(m, acc[0], acc[1]);
@@ -137,14 +201,8 @@ __device__ __forceinline__ void rans_decode_group(const uint32_t *__restrict__ t
   cp_async_wait_all();
 }
 
-// Copy one staged group (n_runs lane-runs of 256 B) to global memory, coalesced.
-__device__ __forceinline__ void copy_stage_to_global(const uint8_t *stage, uint8_t *dst,
-                                                     uint32_t n_runs) {
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t r = 0; r < n_runs; ++r) {
-    const uint2 v = *reinterpret_cast<const uint2 *>(stage + r * kRunStride + lane * 8);
-    *reinterpret_cast<uint2 *>(dst + r * 256 + lane * 8) = v;
-  }
+__device__ __forceinline__ void trap_unless_aligned(uint32_t s, uint32_t align) {
+  if (s & (align - 1)) __trap();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -213,7 +271,8 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__rest
 // ---------------------------------------------------------------------------------------
 // helpers to read the reference's device-side offset table (codec/decoder.cpp:430-463)
 struct ImageStreams {
-  const uint8_t *stream[4];
+  const uint8_t *payload;
+  uint32_t in_off[4];
   uint32_t out_off[4];
   uint32_t palette_bytes;
   uint32_t pal_off;  // offset of this image's palette inside the compact palette scratch
@@ -221,44 +280,50 @@ struct ImageStreams {
 
 __device__ __forceinline__ ImageStreams image_streams(const BatchParams &p, uint32_t b) {
   ImageStreams s;
-  const uint32_t *out_off = reinterpret_cast<const uint32_t *>(p.cmp);
-  const uint32_t *in_off = out_off + 4 * p.n_images;
-  const uint8_t *payload = p.cmp + p.off_region + 2048ull * p.n_images;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    s.out_off[i] = __ldg(out_off + 4 * b + i);
-    s.stream[i] = payload + __ldg(in_off + 4 * b + i);
-  }
-  s.palette_bytes = s.out_off[3] - s.out_off[2];
-  s.pal_off = s.out_off[2] - 7u * p.n_blocks * b - 6u * p.n_blocks;
+  const uint4 *tbl = reinterpret_cast<const uint4 *>(p.cmp);
+  const uint4 oo = __ldg(tbl + b), io = __ldg(tbl + p.n_images + b);
+  s.payload = p.cmp + p.off_region + 2048ull * p.n_images;
+  s.out_off[0] = oo.x; s.out_off[1] = oo.y; s.out_off[2] = oo.z; s.out_off[3] = oo.w;
+  s.in_off[0] = io.x;  s.in_off[1] = io.y;  s.in_off[2] = io.z;  s.in_off[3] = io.w;
+  s.palette_bytes = oo.w - oo.z;
+  s.pal_off = oo.z - 7u * p.n_blocks * b - 6u * p.n_blocks;
   return s;
 }
 
-__device__ __forceinline__ void load_table(uint32_t *dst, const uint32_t *__restrict__ src,
+__device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__restrict__ src,
                                            uint32_t tid, uint32_t n_threads) {
   const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-  for (uint32_t i = tid; i < kTableSize / 4; i += n_threads) d4[i] = __ldg(s4 + i);
+  for (uint32_t i = tid; i < kTableSize / 4; i += n_threads) {
+    const uint4 v = __ldg(s4 + i);
+    sts128(dst_s + 16 * i, v.x, v.y, v.z, v.w);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
-// Palette + index streams.  One warp per rANS group, 4 warps per CTA, all warps of a CTA on
-// the same stream (one table in shared memory).
-//   palette groups: symbols -> compact palette scratch (these are the u32 DXT index words,
-//                   codec/encoder.cpp:100-108)
+// Palette + index streams.  One warp per rANS group, 8 warps per CTA, all warps of a CTA on
+// the same stream (one table in shared memory); no symbol staging, so 6 CTAs fit an SM.
+//   palette groups: symbols go straight to the compact palette scratch (they are the u32 DXT
+//                   index words, codec/encoder.cpp:100-108)
 //   index groups:   symbols are (delta + 128) per DXT block in raster order
-//                   (codec/dxt_image.cpp:610-618); the warp writes the group-local inclusive
-//                   prefix sum of (byte - 128) (codec/decode_indices.cl:24) and the group total.
-constexpr int kSideWarps = 4;
-constexpr int kSideSmem = kTableSize * 4 + kSideWarps * (kRing + kStagePlane);
+//                   (codec/dxt_image.cpp:610-618) and every lane owns 256 consecutive blocks
+//                   (a "run").  Stage 3 (codec/decode_indices.cl:24, idx[i] = sum_{j<=i} d[j])
+//                   is fused behind the decoder: symbols arrive last-to-first, so the lane
+//                   writes S[i] = sum of the deltas AFTER i inside its run, and
+//                   idx[i] = run_end[run] - S[i], where run_end is the inclusive prefix at the
+//                   end of the run (finished by index_carry_kernel).  S is stored mod 2^16 when
+//                   every palette of the batch has <= 65536 entries (idx < 2^16 then makes the
+//                   16-bit difference exact), else as 32 bits.
+constexpr int kSideWarps = 8;
+constexpr int kSideSmem = kSideWarps * kRing + kTableSize * 4;
 
-__global__ void __launch_bounds__(kSideWarps * 32)
+__global__ void __launch_bounds__(kSideWarps * 32, 6)
     side_streams_kernel(const BatchParams p, uint32_t pal_ctas, uint32_t idx_ctas) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_s = smem_u32(smem);
+  trap_unless_aligned(smem_s, kRing);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *ring = smem + kTableSize * 4 + warp * kRing;
-  uint8_t *stage = smem + kTableSize * 4 + kSideWarps * kRing + warp * kStagePlane;
+  const uint32_t ring_s = smem_s + warp * kRing;
+  const uint32_t tab_s = smem_s + kSideWarps * kRing;
 
   const uint32_t per_image = pal_ctas + idx_ctas;
   const uint32_t b = blockIdx.x / per_image;
@@ -270,80 +335,96 @@ __global__ void __launch_bounds__(kSideWarps * 32)
   const uint32_t first = (is_index ? r - pal_ctas : r) * kSideWarps;
   if (first >= n_groups) return;
 
-  load_table(tab, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kSideWarps * 32);
+  load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kSideWarps * 32);
   __syncthreads();
   const uint32_t group = first + warp;
   if (group >= n_groups) return;
-
-  uint32_t bytesum = 0;
-  rans_decode_group(tab, is.stream[type], group, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
-                    [&](int m, uint32_t lo, uint32_t hi) {
-                      *reinterpret_cast<uint2 *>(stage + lane * kRunStride + 248 - 8 * m) =
-                          make_uint2(lo, hi);
-                      bytesum = __dp4a(lo, 0x01010101u, bytesum);
-                      bytesum = __dp4a(hi, 0x01010101u, bytesum);
-                    });
-  __syncwarp();
-
-  if (p.tap_symbols)
-    copy_stage_to_global(stage, p.tap_symbols + is.out_off[type] + static_cast<size_t>(group) * kGroupSyms,
-                         kLanes);
+  const uint8_t *stream = is.payload + (is_index ? is.in_off[3] : is.in_off[2]);
+  const uint32_t out_off = is_index ? is.out_off[3] : is.out_off[2];
+  uint8_t *tap = p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 248
+                               : nullptr;
 
   if (!is_index) {
     const uint64_t off = static_cast<uint64_t>(is.pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
-    if (off + kGroupSyms <= p.palette_cap) copy_stage_to_global(stage, p.palette + off, kLanes);
+    const bool ok = off + kGroupSyms <= p.palette_cap;
+    uint8_t *dst = p.palette + off + lane * kSymsPerLane + 248;
+    rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                            [&](int m, uint32_t lo, uint32_t hi) {
+                              if (ok) *reinterpret_cast<uint2 *>(dst - 8 * m) = make_uint2(lo, hi);
+                              if (tap) *reinterpret_cast<uint2 *>(tap - 8 * m) = make_uint2(lo, hi);
+                            });
     return;
   }
 
-  // lane l holds symbols [256 l, 256 l + 256) of the group = consecutive raster blocks
-  const uint32_t lane_total = bytesum - 128u * kSymsPerLane;
-  uint32_t inc = lane_total;
+  uint32_t sum = 0;  // sum of (byte - 128) over the symbols decoded so far = positions after the current one
+  const size_t run0 = static_cast<size_t>(b) * p.n_blocks + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 248;
+  uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + run0;
+  uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + run0;
+  const bool idx16 = p.idx16 != 0;
+  rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                          [&](int m, uint32_t lo, uint32_t hi) {
+                            if (tap) *reinterpret_cast<uint2 *>(tap - 8 * m) = make_uint2(lo, hi);
+                            uint32_t s[8];
+                            s[7] = sum; sum += ((hi >> 24) & 0xFFu) - 128u;
+                            s[6] = sum; sum += ((hi >> 16) & 0xFFu) - 128u;
+                            s[5] = sum; sum += ((hi >> 8) & 0xFFu) - 128u;
+                            s[4] = sum; sum += (hi & 0xFFu) - 128u;
+                            s[3] = sum; sum += ((lo >> 24) & 0xFFu) - 128u;
+                            s[2] = sum; sum += ((lo >> 16) & 0xFFu) - 128u;
+                            s[1] = sum; sum += ((lo >> 8) & 0xFFu) - 128u;
+                            s[0] = sum; sum += (lo & 0xFFu) - 128u;
+                            if (idx16) {
+                              *reinterpret_cast<uint4 *>(dst16 - 8 * m) =
+                                  make_uint4(__byte_perm(s[0], s[1], 0x5410), __byte_perm(s[2], s[3], 0x5410),
+                                             __byte_perm(s[4], s[5], 0x5410), __byte_perm(s[6], s[7], 0x5410));
+                            } else {
+                              *reinterpret_cast<uint4 *>(dst32 - 8 * m) = make_uint4(s[0], s[1], s[2], s[3]);
+                              *reinterpret_cast<uint4 *>(dst32 - 8 * m + 4) = make_uint4(s[4], s[5], s[6], s[7]);
+                            }
+                          });
+  // group-local inclusive prefix at the end of every run, and the group total
+  uint32_t inc = sum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += n;
   }
+  p.run_end[static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + group * kLanes + lane] = static_cast<int32_t>(inc);
   if (lane == 31) p.idx_total[static_cast<size_t>(b) * p.groups_per_plane + group] = static_cast<int32_t>(inc);
-  uint32_t run = inc - lane_total;
-  int32_t *dst = p.idx_local + static_cast<size_t>(b) * p.n_blocks +
-                 static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane;
-  const uint8_t *src = stage + lane * kRunStride;
-#pragma unroll 2
-  for (int k = 0; k < 32; ++k) {
-    const uint2 w = *reinterpret_cast<const uint2 *>(src + 8 * k);
-    uint32_t o[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      run += ((w.x >> (8 * j)) & 0xFFu) - 128u;
-      o[j] = run;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      run += ((w.y >> (8 * j)) & 0xFFu) - 128u;
-      o[4 + j] = run;
-    }
-    *reinterpret_cast<uint4 *>(dst + 8 * k) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4 *>(dst + 8 * k + 4) = make_uint4(o[4], o[5], o[6], o[7]);
-  }
 }
 
-// Exclusive scan of the per-group totals of one image (the collect_indices passes of
-// codec/decode_indices.cl:66-84 collapse to this).
-__global__ void __launch_bounds__(32) index_carry_kernel(const BatchParams p) {
-  const uint32_t lane = threadIdx.x;
-  const int32_t *tot = p.idx_total + static_cast<size_t>(blockIdx.x) * p.groups_per_plane;
-  int32_t *car = p.idx_carry + static_cast<size_t>(blockIdx.x) * p.groups_per_plane;
-  uint32_t base = 0;
-  for (uint32_t i = 0; i < p.groups_per_plane; i += 32) {
-    const uint32_t v = (i + lane < p.groups_per_plane) ? static_cast<uint32_t>(tot[i + lane]) : 0u;
+// The cross-group part of stage 3 (what the collect_indices passes of
+// codec/decode_indices.cl:66-84 do): exclusive scan of the group totals of one image, added to
+// the group-local run ends.  One CTA per image.
+__global__ void __launch_bounds__(256) index_carry_kernel(const BatchParams p) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_base;
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int32_t *tot = p.idx_total + static_cast<size_t>(blockIdx.x) * p.groups_per_plane;
+  int32_t *run_end = p.run_end + static_cast<size_t>(blockIdx.x) * (p.n_blocks / kSymsPerLane);
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < p.groups_per_plane; i0 += 256) {
+    const uint32_t i = i0 + t;
+    const uint32_t v = i < p.groups_per_plane ? static_cast<uint32_t>(tot[i]) : 0u;
     uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
       if (lane >= d) inc += n;
     }
-    if (i + lane < p.groups_per_plane) car[i + lane] = static_cast<int32_t>(base + inc - v);
-    base += __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = s_base;
+    for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+    const uint32_t carry = base + inc - v;  // exclusive
+    if (i < p.groups_per_plane) {
+      // the 32 runs of group i
+      for (uint32_t l = 0; l < kLanes; ++l) run_end[i * kLanes + l] += static_cast<int32_t>(carry);
+    }
+    __syncthreads();
+    if (t == 255) s_base = base + inc;
+    __syncthreads();
   }
 }
 
@@ -372,40 +453,64 @@ __device__ __forceinline__ void inverse_lift(int (&v)[LEN]) {
   for (int i = 0; i < LEN; ++i) v[i] = o[i];
 }
 
-constexpr int kWRow = 34;                       // int16 per work-tile row (17 words: odd stride)
-constexpr int kWBytes = kTile * kWRow * 2;      // 2176 B per warp
+// Work tiles (int16, per warp).  Intermediates are bounded by 128 + 672 per level (<= 3488
+// after five levels) for ANY input bytes, so int16 storage is exact.
+//   Wlow: the 16x16 corners of two planes, 32 rows of 32 B; the two 16-byte chunks of row
+//         `rid` are swapped when (rid >> 2) & 1, which makes lane = row 16-byte accesses and
+//         lane = column 2-byte accesses conflict free without padding.
+//   W   : one 32x32 tile, 32 rows of 64 B, chunk j of row r stored at j ^ ((r >> 1) & 3).
+constexpr int kWBytes = 2048;
+constexpr int kWlowBytes = 1024;
+constexpr int kWarpWork = kWBytes + kWlowBytes;
 
-// One level on the top-left LEN x LEN corner of the warp's int16 work tile: rows then
-// columns (codec/inverse_wavelet.cl:113-172).  Intermediates are bounded by 128 + 672 per
-// level (<= 3488 after five levels) for ANY input bytes, so int16 storage is exact.
+// levels 2..16 on two planes at once: lanes 0-15 own plane A, lanes 16-31 plane B
 template <int LEN>
-__device__ __forceinline__ void wavelet_rows(int16_t *W, uint32_t lane) {
-  if (lane < LEN) {
-    uint32_t *row = reinterpret_cast<uint32_t *>(W + lane * kWRow);
+__device__ __forceinline__ void low_level(uint32_t wl_s, uint32_t lane) {
+  const uint32_t rc = lane & 15;  // row in the row pass, column in the column pass
+  // rows
+  if (rc < LEN) {
+    const uint32_t row = wl_s + lane * 32 + (((lane >> 2) & 1) << 4);  // logical chunk 0
     int v[LEN];
+    if (LEN == 16) {
+      const uint4 a = lds128(row), b = lds128(row ^ 16);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < LEN / 2; ++i) {
-      const uint32_t w = row[i];
-      v[2 * i] = static_cast<int16_t>(w & 0xFFFFu);
-      v[2 * i + 1] = static_cast<int32_t>(w) >> 16;
+      for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
+    } else if (LEN == 8) {
+      const uint4 a = lds128(row);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
+    } else if (LEN == 4) {
+      const uint2 a = lds64(row);
+      v[0] = lo16(a.x); v[1] = hi16(a.x); v[2] = lo16(a.y); v[3] = hi16(a.y);
+    } else {
+      const uint32_t a = lds32(row);
+      v[0] = lo16(a); v[1] = hi16(a);
     }
     inverse_lift<LEN>(v);
-#pragma unroll
-    for (int i = 0; i < LEN / 2; ++i)
-      row[i] = (static_cast<uint32_t>(v[2 * i]) & 0xFFFFu) | (static_cast<uint32_t>(v[2 * i + 1]) << 16);
+    if (LEN == 16) {
+      sts128(row, pack16(v[0], v[1]), pack16(v[2], v[3]), pack16(v[4], v[5]), pack16(v[6], v[7]));
+      sts128(row ^ 16, pack16(v[8], v[9]), pack16(v[10], v[11]), pack16(v[12], v[13]), pack16(v[14], v[15]));
+    } else if (LEN == 8) {
+      sts128(row, pack16(v[0], v[1]), pack16(v[2], v[3]), pack16(v[4], v[5]), pack16(v[6], v[7]));
+    } else if (LEN == 4) {
+      sts64(row, pack16(v[0], v[1]), pack16(v[2], v[3]));
+    } else {
+      sts32(row, pack16(v[0], v[1]));
+    }
   }
   __syncwarp();
-}
-
-template <int LEN>
-__device__ __forceinline__ void wavelet_cols(int16_t *W, uint32_t lane) {
-  if (lane < LEN) {
+  // columns
+  if (rc < LEN) {
+    const uint32_t base = wl_s + (lane & 16) * 32;  // plane A or B
+    const uint32_t col[2] = {base + (((rc >> 3) ^ 0) << 4) + (rc & 7) * 2, base + (((rc >> 3) ^ 1) << 4) + (rc & 7) * 2};
     int v[LEN];
 #pragma unroll
-    for (int i = 0; i < LEN; ++i) v[i] = W[i * kWRow + lane];
+    for (int i = 0; i < LEN; ++i) v[i] = lds_s16(col[(i >> 2) & 1] + i * 32);
     inverse_lift<LEN>(v);
 #pragma unroll
-    for (int i = 0; i < LEN; ++i) W[i * kWRow + lane] = static_cast<int16_t>(v[i]);
+    for (int i = 0; i < LEN; ++i) sts16(col[(i >> 2) & 1] + i * 32, static_cast<uint32_t>(v[i]));
   }
   __syncwarp();
 }
@@ -417,65 +522,62 @@ __device__ __forceinline__ void ycocg_to_rgb(int y, int co, int cg, int &r, int 
   b = (t - co) / 2;
   r = b + co;
 }
-__device__ __forceinline__ uint32_t pack565(int y, int co, int cg) {
+__device__ __forceinline__ uint32_t pack565(int y, int co, int cg) {  // low 16 bits valid
   int r, g, b;
   ycocg_to_rgb(y, co, cg, r, g, b);
-  return ((static_cast<uint32_t>(r) << 11) | (static_cast<uint32_t>(g) << 5) | static_cast<uint32_t>(b)) & 0xFFFFu;
-}
-__device__ __forceinline__ int sbyte(uint32_t w, int j) {
-  return static_cast<int8_t>((w >> (8 * j)) & 0xFFu);
+  return (static_cast<uint32_t>(r) << 11) | (static_cast<uint32_t>(g) << 5) | static_cast<uint32_t>(b);
 }
 
 // ---------------------------------------------------------------------------------------
 // The fused endpoint-plane kernel.  CTA (b, g) owns tiles [8g, 8g+8) of image b in all six
 // planes [Y1,Y2,Co1,Cg1,Co2,Cg2] (codec/assemble.cl:27-37) = one rANS group per plane.
 //   phase 1: warps 0..5 rANS-decode one group each into shared memory (48 KB of symbols)
-//   phase 2: warp t runs the 5-level inverse wavelet on tile t of every plane in a private
-//            int16 work tile (rows in registers, lane = row, then lane = column)
+//   phase 2: warp t runs the 5-level inverse wavelet on tile t of every plane; levels 2..16 on
+//            two planes at a time (lane = plane x row / plane x column), level 32 per plane
+//            (lane = row in registers, then lane = column)
 //   phase 3: warp t assembles the 1024 DXT1 blocks (or RGB8 texels) of tile t with coalesced
-//            16-byte stores; the palette word comes from the index prefix written by
-//            side_streams_kernel plus the per-group carry.
+//            16-byte stores; the palette index is run_end - S (see side_streams_kernel).
+// Shared memory (1 KiB aligned): [6 rings][2 tables][2 KB] (phase 2 reuses these 24 KB as
+// 8 x (W + Wlow)) [6 staged groups].
 constexpr int kFusedWarps = 8;
-constexpr int kFusedAux = 2 * kTableSize * 4 + 6 * kRing;  // tables + rings, reused by work tiles
-static_assert(kFusedAux >= kFusedWarps * kWBytes, "work tiles must fit in the aliased region");
-constexpr int kFusedSmem = 6 * kStagePlane + kFusedAux;    // 73216 B -> 3 CTAs / SM
+constexpr int kFusedAux = kFusedWarps * kWarpWork;  // 24576
+static_assert(kFusedAux >= 6 * kRing + 2 * kTableSize * 4, "phase 1 buffers must fit the aliased region");
+constexpr int kFusedSmem = kFusedAux + 6 * kStagePlane;  // 75264 B -> 3 CTAs / SM
 
 template <int RGB>
 __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const BatchParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t *stage = smem;
-  uint8_t *aux = smem + 6 * kStagePlane;
-  uint32_t *tabs = reinterpret_cast<uint32_t *>(aux);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_s = smem_u32(smem);
+  trap_unless_aligned(smem_s, kRing);
+  const uint32_t stage_s = smem_s + kFusedAux;
+  const uint32_t tabs_s = smem_s + 6 * kRing;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b = blockIdx.x / p.groups_per_plane;
   const uint32_t g = blockIdx.x % p.groups_per_plane;
   const ImageStreams is = image_streams(p, b);
 
   // Y table and chroma table of this image
-  load_table(tabs, p.tables + (4ull * b + 0) * kTableSize, threadIdx.x, kFusedWarps * 32);
-  load_table(tabs + kTableSize, p.tables + (4ull * b + 1) * kTableSize, threadIdx.x, kFusedWarps * 32);
+  load_table(tabs_s, p.tables + (4ull * b + 0) * kTableSize, threadIdx.x, kFusedWarps * 32);
+  load_table(tabs_s + kTableSize * 4, p.tables + (4ull * b + 1) * kTableSize, threadIdx.x, kFusedWarps * 32);
   __syncthreads();
 
   if (warp < 6) {
     // Y stream = Y1 || Y2, chroma stream = Co1 || Cg1 || Co2 || Cg2 (codec/encoder.cpp:87,93-95)
-    const uint32_t type = warp < 2 ? 0u : 1u;
-    const uint32_t group = (warp < 2 ? warp : warp - 2) * p.groups_per_plane + g;
-    uint8_t *my_stage = stage + warp * kStagePlane + lane * kRunStride + 248;
-    rans_decode_group(tabs + type * kTableSize, is.stream[type], group, kLanes,
-                      aux + 2 * kTableSize * 4 + warp * kRing, p.cmp, p.cmp + p.cmp_bytes,
-                      [&](int m, uint32_t lo, uint32_t hi) {
-                        *reinterpret_cast<uint2 *>(my_stage - 8 * m) = make_uint2(lo, hi);
-                      });
+    const bool chroma = warp >= 2;
+    const uint32_t group = (chroma ? warp - 2 : warp) * p.groups_per_plane + g;
+    const uint32_t my_stage = stage_s + warp * kStagePlane + lane * kRunStride + 248;
+    rans_decode_group<true>(tabs_s + (chroma ? kTableSize * 4 : 0), is.payload + (chroma ? is.in_off[1] : is.in_off[0]),
+                            group, kLanes, smem_s + warp * kRing, p.cmp, p.cmp + p.cmp_bytes,
+                            [&](int m, uint32_t lo, uint32_t hi) { sts64(my_stage - 8 * m, lo, hi); });
   }
   __syncthreads();
 
   if (p.tap_symbols) {
     for (uint32_t pl = 0; pl < 6; ++pl) {
-      const uint32_t type = pl < 2 ? 0u : 1u;
       const uint32_t group = (pl < 2 ? pl : pl - 2) * p.groups_per_plane + g;
-      uint8_t *dst = p.tap_symbols + is.out_off[type] + static_cast<size_t>(group) * kGroupSyms;
+      uint8_t *dst = p.tap_symbols + (pl < 2 ? is.out_off[0] : is.out_off[1]) + static_cast<size_t>(group) * kGroupSyms;
       for (uint32_t r = warp; r < kLanes; r += kFusedWarps) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(stage + pl * kStagePlane + r * kRunStride + lane * 8);
+        const uint2 v = lds64(stage_s + pl * kStagePlane + r * kRunStride + lane * 8);
         *reinterpret_cast<uint2 *>(dst + r * 256 + lane * 8) = v;
       }
     }
@@ -486,138 +588,202 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t tile = g * 8 + warp;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
-  int16_t *W = reinterpret_cast<int16_t *>(aux + warp * kWBytes);
-  uint8_t *tile_stage = stage + 4 * warp * kRunStride;  // + plane * kStagePlane
+  const uint32_t w_s = smem_s + warp * kWarpWork;
+  const uint32_t wl_s = w_s + kWBytes;
+  const uint32_t tile_s = stage_s + 4 * warp * kRunStride;  // + plane * kStagePlane
+  // byte offset of row `lane` (row pass) / of rows 0..15 of the plane pair (corner load)
+  const uint32_t row_off = (lane >> 3) * kRunStride + (lane & 7) * 32;
 
-  for (uint32_t pl = 0; pl < 6; ++pl) {
-    uint8_t *ts = tile_stage + pl * kStagePlane;
-    // bytes -> (byte - 128) as int16, codec/inverse_wavelet.cl:97-100
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const uint32_t row = 4 * s + (lane >> 3), col = 4 * (lane & 7);
-      const uint32_t w = *reinterpret_cast<const uint32_t *>(ts + (row >> 3) * kRunStride + (row & 7) * 32 + col);
-      const int v0 = static_cast<int>(w & 0xFFu) - 128, v1 = static_cast<int>((w >> 8) & 0xFFu) - 128;
-      const int v2 = static_cast<int>((w >> 16) & 0xFFu) - 128, v3 = static_cast<int>(w >> 24) - 128;
-      uint32_t *d = reinterpret_cast<uint32_t *>(W + row * kWRow + col);
-      d[0] = (static_cast<uint32_t>(v0) & 0xFFFFu) | (static_cast<uint32_t>(v1) << 16);
-      d[1] = (static_cast<uint32_t>(v2) & 0xFFFFu) | (static_cast<uint32_t>(v3) << 16);
-    }
-    __syncwarp();
-    wavelet_rows<2>(W, lane);
-    wavelet_cols<2>(W, lane);
-    wavelet_rows<4>(W, lane);
-    wavelet_cols<4>(W, lane);
-    wavelet_rows<8>(W, lane);
-    wavelet_cols<8>(W, lane);
-    wavelet_rows<16>(W, lane);
-    wavelet_cols<16>(W, lane);
-    wavelet_rows<32>(W, lane);
-    // last column pass: (char) truncation (codec/inverse_wavelet.cl:188-190) back into the
-    // staging slot of this tile, row-major bytes
+#pragma unroll 1
+  for (uint32_t pair = 0; pair < 3; ++pair) {
+    // corners: lane -> (plane pair*2 + lane/16, row lane%16), bytes -> (byte - 128) as int16
     {
-      int v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = W[i * kWRow + lane];
-      inverse_lift<32>(v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) ts[(i >> 3) * kRunStride + (i & 7) * 32 + lane] = static_cast<uint8_t>(v[i]);
-      if (p.tap_planes) {
-        int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + pl) * p.n_blocks +
-                     static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tp[static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i]);
-      }
+      const uint32_t r = lane & 15;
+      const uint32_t src = tile_s + (2 * pair + (lane >> 4)) * kStagePlane + (r >> 3) * kRunStride + (r & 7) * 32;
+      const uint2 a = lds64(src), c = lds64(src + 8);
+      const uint32_t x0 = a.x ^ 0x80808080u, x1 = a.y ^ 0x80808080u, x2 = c.x ^ 0x80808080u, x3 = c.y ^ 0x80808080u;
+      const uint32_t row = wl_s + lane * 32 + (((lane >> 2) & 1) << 4);
+      sts128(row, sext_byte_pair<0>(x0), sext_byte_pair<2>(x0), sext_byte_pair<0>(x1), sext_byte_pair<2>(x1));
+      sts128(row ^ 16, sext_byte_pair<0>(x2), sext_byte_pair<2>(x2), sext_byte_pair<0>(x3), sext_byte_pair<2>(x3));
     }
     __syncwarp();
+    low_level<2>(wl_s, lane);
+    low_level<4>(wl_s, lane);
+    low_level<8>(wl_s, lane);
+    low_level<16>(wl_s, lane);
+
+#pragma unroll 1
+    for (uint32_t q = 0; q < 2; ++q) {
+      const uint32_t pl = 2 * pair + q;
+      const uint32_t ts = tile_s + pl * kStagePlane;
+      // ---- level 32, rows: lane = row
+      {
+        int v[32];
+        const uint32_t src = ts + row_off;
+        if (lane < 16) {  // low half of rows 0..15 = the 16x16 result of the lower levels
+          const uint32_t rid = q * 16 + lane;
+          const uint32_t row = wl_s + rid * 32 + (((rid >> 2) & 1) << 4);
+          const uint4 a = lds128(row), c = lds128(row ^ 16);
+          const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
+        } else {
+          const uint2 a = lds64(src), c = lds64(src + 8);
+          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, c.x ^ 0x80808080u, c.y ^ 0x80808080u};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[4 * i] = sext_byte<0>(x[i]); v[4 * i + 1] = sext_byte<1>(x[i]);
+            v[4 * i + 2] = sext_byte<2>(x[i]); v[4 * i + 3] = sext_byte<3>(x[i]);
+          }
+        }
+        {
+          const uint2 a = lds64(src + 16), c = lds64(src + 24);
+          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, c.x ^ 0x80808080u, c.y ^ 0x80808080u};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[16 + 4 * i] = sext_byte<0>(x[i]); v[16 + 4 * i + 1] = sext_byte<1>(x[i]);
+            v[16 + 4 * i + 2] = sext_byte<2>(x[i]); v[16 + 4 * i + 3] = sext_byte<3>(x[i]);
+          }
+        }
+        inverse_lift<32>(v);
+        const uint32_t wrow = w_s + lane * 64 + (((lane >> 1) & 3) << 4);  // logical chunk 0
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(wrow ^ (j << 4), pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
+                 pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
+      }
+      __syncwarp();
+      // ---- level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
+      // back into the staging slot of this tile as row-major bytes
+      {
+        uint32_t col[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) col[s] = w_s + ((((lane >> 3) ^ s) & 3) << 4) + (lane & 7) * 2;
+        int v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = lds_s16(col[(i >> 1) & 3] + i * 64);
+        inverse_lift<32>(v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sts8(ts + (i >> 3) * kRunStride + (i & 7) * 32 + lane, static_cast<uint32_t>(v[i]));
+        if (p.tap_planes) {
+          int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + pl) * p.n_blocks +
+                       static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tp[static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i]);
+        }
+      }
+      __syncwarp();
+    }
   }
 
   // ---- phase 3: assembly, codec/assemble.cl:64-129 -------------------------------------
   const uint32_t n_entries = is.palette_bytes / 4;
   const bool pal_ok = static_cast<uint64_t>(is.pal_off) + is.palette_bytes <= p.palette_cap && n_entries > 0;
   const uint32_t *pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? is.pal_off : 0));
-  const int32_t *loc_base = p.idx_local + static_cast<size_t>(b) * p.n_blocks;
-  const int32_t *carry_base = p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane;
+  const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
+  const uint32_t tile_block0 = ty * kTile * p.blocks_x + tx * kTile;
+  const int32_t *run_end = p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane);
+  const bool idx16 = p.idx16 != 0;
 
 #pragma unroll 1
   for (int k = 0; k < 8; ++k) {
     const uint32_t row = 4 * k + (lane >> 3), col = 4 * (lane & 7);
-    const uint32_t gidx = (ty * kTile + row) * p.blocks_x + tx * kTile + col;
+    const uint32_t gidx = tile_block0 + row * p.blocks_x + col;
+    const uint32_t slot = tile_s + (row >> 3) * kRunStride + (row & 7) * 32 + col;
     uint32_t pw[6];
 #pragma unroll
-    for (int pl = 0; pl < 6; ++pl)
-      pw[pl] = *reinterpret_cast<const uint32_t *>(tile_stage + pl * kStagePlane + (row >> 3) * kRunStride +
-                                                   (row & 7) * 32 + col);
-    const int4 loc = __ldg(reinterpret_cast<const int4 *>(loc_base + gidx));
-    const uint32_t carry = static_cast<uint32_t>(__ldg(carry_base + gidx / kGroupSyms));
-    const uint32_t idx[4] = {carry + static_cast<uint32_t>(loc.x), carry + static_cast<uint32_t>(loc.y),
-                             carry + static_cast<uint32_t>(loc.z), carry + static_cast<uint32_t>(loc.w)};
-    if (p.tap_indices)
-      *reinterpret_cast<uint4 *>(p.tap_indices + static_cast<size_t>(b) * p.n_blocks + gidx) =
-          make_uint4(idx[0], idx[1], idx[2], idx[3]);
-    uint32_t word[4];
+    for (int pl = 0; pl < 6; ++pl) pw[pl] = lds32(slot + pl * kStagePlane);
+    uint32_t sfx[4];
+    if (idx16) {
+      const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(p.idx_s) + img_block0 + gidx));
+      sfx[0] = sv.x & 0xFFFFu; sfx[1] = sv.x >> 16; sfx[2] = sv.y & 0xFFFFu; sfx[3] = sv.y >> 16;
+    } else {
+      const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + img_block0 + gidx));
+      sfx[0] = sv.x; sfx[1] = sv.y; sfx[2] = sv.z; sfx[3] = sv.w;
+    }
+    const uint32_t re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
+    uint32_t idx[4], word[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
+    for (int j = 0; j < 4; ++j) {
+      idx[j] = re - sfx[j];
+      if (idx16) idx[j] &= 0xFFFFu;
+      word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
+    }
+    if (p.tap_indices)
+      *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
+
+    int y1[4], y2[4], co1[4], cg1[4], co2[4], cg2[4];
+    y1[0] = sext_byte<0>(pw[0]); y1[1] = sext_byte<1>(pw[0]); y1[2] = sext_byte<2>(pw[0]); y1[3] = sext_byte<3>(pw[0]);
+    y2[0] = sext_byte<0>(pw[1]); y2[1] = sext_byte<1>(pw[1]); y2[2] = sext_byte<2>(pw[1]); y2[3] = sext_byte<3>(pw[1]);
+    co1[0] = sext_byte<0>(pw[2]); co1[1] = sext_byte<1>(pw[2]); co1[2] = sext_byte<2>(pw[2]); co1[3] = sext_byte<3>(pw[2]);
+    cg1[0] = sext_byte<0>(pw[3]); cg1[1] = sext_byte<1>(pw[3]); cg1[2] = sext_byte<2>(pw[3]); cg1[3] = sext_byte<3>(pw[3]);
+    co2[0] = sext_byte<0>(pw[4]); co2[1] = sext_byte<1>(pw[4]); co2[2] = sext_byte<2>(pw[4]); co2[3] = sext_byte<3>(pw[4]);
+    cg2[0] = sext_byte<0>(pw[5]); cg2[1] = sext_byte<1>(pw[5]); cg2[2] = sext_byte<2>(pw[5]); cg2[3] = sext_byte<3>(pw[5]);
 
     if (!RGB) {
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t ep1 = pack565(sbyte(pw[0], j), sbyte(pw[2], j), sbyte(pw[3], j));
-        const uint32_t ep2 = pack565(sbyte(pw[1], j), sbyte(pw[4], j), sbyte(pw[5], j));
-        o[2 * j] = ep1 | (ep2 << 16);  // PhysicalDXTBlock, codec/dxt_image.h:14-21
+        // PhysicalDXTBlock (codec/dxt_image.h:14-21): u16 ep1, u16 ep2, u32 interpolation
+        o[2 * j] = __byte_perm(pack565(y1[j], co1[j], cg1[j]), pack565(y2[j], co2[j], cg2[j]), 0x5410);
         o[2 * j + 1] = word[j];
       }
-      uint8_t *dst = p.out + (static_cast<size_t>(b) * p.n_blocks + gidx) * 8;
-      st_global_cs_v4(dst, make_uint4(o[0], o[1], o[2], o[3]));
-      st_global_cs_v4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+      uint8_t *dst = p.out + (img_block0 + gidx) * 8;
+      st_global_cs_v4(dst, o[0], o[1], o[2], o[3]);
+      st_global_cs_v4(dst + 16, o[4], o[5], o[6], o[7]);
     } else {
       // assemble_rgb: 565 -> 888 by bit replication, always the 4-colour palette
       // (codec/assemble.cl:102-111); 16 texels per block, raster RGB8 (:117-128)
-      uint8_t texel[4][4][3];  // [block j][palette entry][channel]
+      uint32_t pal4[4][4];  // [block j][palette entry] = r | g << 8 | b << 16 (uchar-truncated)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int c0[3], c1[3];
-        ycocg_to_rgb(sbyte(pw[0], j), sbyte(pw[2], j), sbyte(pw[3], j), c0[0], c0[1], c0[2]);
-        ycocg_to_rgb(sbyte(pw[1], j), sbyte(pw[4], j), sbyte(pw[5], j), c1[0], c1[1], c1[2]);
+        ycocg_to_rgb(y1[j], co1[j], cg1[j], c0[0], c0[1], c0[2]);
+        ycocg_to_rgb(y2[j], co2[j], cg2[j], c1[0], c1[1], c1[2]);
         c0[0] = static_cast<int>((static_cast<uint32_t>(c0[0]) << 3) | static_cast<uint32_t>(c0[0] >> 2));
         c0[1] = static_cast<int>((static_cast<uint32_t>(c0[1]) << 2) | static_cast<uint32_t>(c0[1] >> 4));
         c0[2] = static_cast<int>((static_cast<uint32_t>(c0[2]) << 3) | static_cast<uint32_t>(c0[2] >> 2));
         c1[0] = static_cast<int>((static_cast<uint32_t>(c1[0]) << 3) | static_cast<uint32_t>(c1[0] >> 2));
         c1[1] = static_cast<int>((static_cast<uint32_t>(c1[1]) << 2) | static_cast<uint32_t>(c1[1] >> 4));
         c1[2] = static_cast<int>((static_cast<uint32_t>(c1[2]) << 3) | static_cast<uint32_t>(c1[2] >> 2));
+        uint32_t e[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          texel[j][0][c] = static_cast<uint8_t>(c0[c]);
-          texel[j][1][c] = static_cast<uint8_t>(c1[c]);
-          texel[j][2][c] = static_cast<uint8_t>((2 * c0[c] + c1[c]) / 3);
-          texel[j][3][c] = static_cast<uint8_t>((c0[c] + 2 * c1[c]) / 3);
+          e[0] |= (static_cast<uint32_t>(c0[c]) & 0xFFu) << (8 * c);
+          e[1] |= (static_cast<uint32_t>(c1[c]) & 0xFFu) << (8 * c);
+          e[2] |= (static_cast<uint32_t>((2 * c0[c] + c1[c]) / 3) & 0xFFu) << (8 * c);
+          e[3] |= (static_cast<uint32_t>((c0[c] + 2 * c1[c]) / 3) & 0xFFu) << (8 * c);
         }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) pal4[j][s] = e[s];
       }
       const size_t img_w = 4ull * p.blocks_x;
       uint8_t *img = p.out + static_cast<size_t>(b) * p.n_blocks * 48;
       const size_t x0 = 4ull * (tx * kTile + col), y0 = 4ull * (ty * kTile + row);
 #pragma unroll
       for (int yy = 0; yy < 4; ++yy) {
-        uint32_t bytes[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) bytes[i] = 0;
+        uint32_t t[16];  // 16 texels of this texel row, r | g << 8 | b << 16
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
           for (int xx = 0; xx < 4; ++xx) {
             const uint32_t sel = (word[j] >> (2 * (4 * yy + xx))) & 3u;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const uint32_t v = sel == 0 ? texel[j][0][c] : sel == 1 ? texel[j][1][c] : sel == 2 ? texel[j][2][c] : texel[j][3][c];
-              const int pos = 12 * j + 3 * xx + c;
-              bytes[pos >> 2] |= v << (8 * (pos & 3));
-            }
+            const uint32_t lo = (sel & 1u) ? pal4[j][1] : pal4[j][0];
+            const uint32_t hi = (sel & 1u) ? pal4[j][3] : pal4[j][2];
+            t[4 * j + xx] = (sel & 2u) ? hi : lo;
           }
         }
+        uint32_t wds[12];  // 48 bytes: 16 x RGB
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          wds[3 * i + 0] = t[4 * i] | (t[4 * i + 1] << 24);
+          wds[3 * i + 1] = (t[4 * i + 1] >> 8) | (t[4 * i + 2] << 16);
+          wds[3 * i + 2] = (t[4 * i + 2] >> 16) | (t[4 * i + 3] << 8);
+        }
         uint8_t *dst = img + 3 * (img_w * (y0 + yy) + x0);
-        st_global_cs_v4(dst, make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]));
-        st_global_cs_v4(dst + 16, make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]));
-        st_global_cs_v4(dst + 32, make_uint4(bytes[8], bytes[9], bytes[10], bytes[11]));
+        st_global_cs_v4(dst, wds[0], wds[1], wds[2], wds[3]);
+        st_global_cs_v4(dst + 16, wds[4], wds[5], wds[6], wds[7]);
+        st_global_cs_v4(dst + 32, wds[8], wds[9], wds[10], wds[11]);
       }
     }
   }
@@ -627,28 +793,28 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
 // Standalone decode of [u32 end_offset[n_groups]][groups] with 1..32 interleaved lanes and a
 // single table: the `ans_decode` kernel of ans/ans_decode.cl:76-95 as driven by
 // ans/ans_ocl.cpp:159-345.  Output: group * n_lanes * 256 + lane * 256 + position.
-constexpr int kPlainWarps = 4;
-constexpr int kPlainSmem = kTableSize * 4 + kPlainWarps * (kRing + kStagePlane);
+constexpr int kPlainWarps = 8;
+constexpr int kPlainSmem = kPlainWarps * kRing + kTableSize * 4;
 
 __global__ void __launch_bounds__(kPlainWarps * 32)
     ans_decode_plain_kernel(const uint32_t *__restrict__ table, const uint8_t *__restrict__ data,
                             uint64_t data_bytes, uint32_t n_groups, uint32_t n_lanes,
                             uint8_t *__restrict__ out) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_s = smem_u32(smem);
+  trap_unless_aligned(smem_s, kRing);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *ring = smem + kTableSize * 4 + warp * kRing;
-  uint8_t *stage = smem + kTableSize * 4 + kPlainWarps * kRing + warp * kStagePlane;
-  load_table(tab, table, threadIdx.x, kPlainWarps * 32);
+  const uint32_t tab_s = smem_s + kPlainWarps * kRing;
+  load_table(tab_s, table, threadIdx.x, kPlainWarps * 32);
   __syncthreads();
   const uint32_t group = blockIdx.x * kPlainWarps + warp;
   if (group >= n_groups) return;
-  rans_decode_group(tab, data, group, n_lanes, ring, data, data + data_bytes,
-                    [&](int m, uint32_t lo, uint32_t hi) {
-                      *reinterpret_cast<uint2 *>(stage + lane * kRunStride + 248 - 8 * m) = make_uint2(lo, hi);
-                    });
-  __syncwarp();
-  copy_stage_to_global(stage, out + static_cast<size_t>(group) * n_lanes * kSymsPerLane, n_lanes);
+  uint8_t *dst = out + (static_cast<size_t>(group) * n_lanes + lane) * kSymsPerLane + 248;
+  const bool active = lane < n_lanes;
+  rans_decode_group<false>(tab_s, data, group, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
+                           [&](int m, uint32_t lo, uint32_t hi) {
+                             if (active) *reinterpret_cast<uint2 *>(dst - 8 * m) = make_uint2(lo, hi);
+                           });
 }
 
 }  // namespace
@@ -695,7 +861,7 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
-  index_carry_kernel<<<p.n_images, 32, 0, s>>>(p);
+  index_carry_kernel<<<p.n_images, 256, 0, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;

@@ -45,9 +45,10 @@ struct BatchParams {
   uint32_t *tables;          // [B][4][2048] packed entries
   uint8_t *palette;          // compact: image b at pal_off(b) = out_off[4b+2] - 7N*b - 6N
   uint64_t palette_cap;      // bytes available in `palette`
-  int32_t *idx_local;        // [B][N]   group-local inclusive prefix of (delta - 128)
+  void *idx_s;               // [B][N] u16 or u32: sum of the index deltas after block i in its 256-block run
+  uint32_t idx16;            // 1: idx_s holds u16 (every palette <= 65536 entries), 0: u32
+  int32_t *run_end;          // [B][N/256] inclusive index prefix at the end of every run
   int32_t *idx_total;        // [B][N/8192] sum of every index group
-  int32_t *idx_carry;        // [B][N/8192] exclusive scan of idx_total
   // outputs
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
   // optional taps for the stage parity tests (NULL in production)
