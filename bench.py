@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=32, help="distinct encoded images tiled to the batch")
     ap.add_argument("--page", type=int, default=32, help="images per page on the e2e path")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: every GPU decodes the whole configured batch; strong: the batch is sharded, "
+                         "image i to rank i mod N")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample")
@@ -220,10 +223,16 @@ def main():
     import gst_fixtures as fx
     from gst_b200.capi import check, lib
 
+    from gst_b200.shard import reduce_job, shard_indices
+
     dec = gst_b200.Decoder(local_rank)
     distinct = min(args.distinct, images)
     files, goldens = load_streams(args.config, width, height, distinct, rank, world)
-    order = [(i + rank) % distinct for i in range(images)]  # ranks start at different images
+    if args.scaling == "strong" and world > 1:
+        order = [i % distinct for i in shard_indices(images, rank, world)]  # image i -> rank i mod N
+        images = len(order)
+    else:
+        order = [(i + rank) % distinct for i in range(images)]  # ranks start at different images
     batch = [files[j] for j in order]
 
     # ---- device-resident inputs ---------------------------------------------------------
@@ -277,15 +286,13 @@ def main():
     dec.profile(False)
     ms_total = ev0.elapsed_ms(ev1)
     kernel_ms, calls = dec.profile_read()
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-
     texels_rank = float(width) * height * images
     cmp_rank = float(sum(f.size - 28 for f in batch))
     alg_bytes_rank = cmp_rank + 8.0 * N * images  # (file - 28) + W*H/2 per image
+    # whole job: max over ranks of the device time, sum over ranks of the units processed
+    ms_total, (texels_job, cmp_job, h2d_job, d2h_job) = reduce_job(
+        ms_total, [texels_rank, cmp_rank, float(packed.size), 8.0 * N * images])
+    ms_step = ms_total / args.steps
 
     # ---- end to end: host .gst buffers -> host DXT1 blocks ---------------------------------
     e2e = None
@@ -312,14 +319,11 @@ def main():
             e2e_step()
         barrier()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": texels_rank * world * e2e_steps / dt / 1e9, "unit": "GTexel/s",
-               "h2d_bytes_per_step": int(packed.size) * world, "d2h_bytes_per_step": int(8 * N * images) * world,
+        dt, _ = reduce_job(dt, [])
+        e2e = {"value": texels_job * e2e_steps / dt / 1e9, "unit": "GTexel/s",
+               "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(d2h_job),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
-               "compressed_gb_s": cmp_rank * world * e2e_steps / dt / 1e9,
+               "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
     clocks = sampler.stop()
 
@@ -348,10 +352,11 @@ def main():
         achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
         step_gbs = alg_bytes_rank / (ms_step * 1e-3) / 1e9
         line = {
-            "metric": "decoded GTexel/s (.gst -> DXT1)", "value": texels_rank * world / (ms_step * 1e-3) / 1e9,
-            "unit": "GTexel/s", "compressed_gb_s": cmp_rank * world / (ms_step * 1e-3) / 1e9,
+            "metric": "decoded GTexel/s (.gst -> DXT1)", "value": texels_job / (ms_step * 1e-3) / 1e9,
+            "unit": "GTexel/s", "compressed_gb_s": cmp_job / (ms_step * 1e-3) / 1e9,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (integer only)",
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "u8/i32 (integer only)",
             "data": "synthetic",
             "config": {"workload": name, "width": width, "height": height, "images_per_gpu": images,
                        "distinct_images": distinct, "bits_per_texel": 8.0 * cmp_rank / texels_rank,

@@ -12,9 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgst_cuda.so")
-SOURCES = ["gst_kernels.cu", "gst_capi.cu", "gentc_facade.cpp"]
-DEPS = SOURCES + ["gst_kernels.cuh", os.path.join("..", "..", "include", "gst_cuda.h"),
-                  os.path.join("..", "..", "include", "gst_decoder.hpp")]
+SOURCES = ["gst_kernels.cu", "gst_capi.cu"]
+DEPS = SOURCES + ["gst_kernels.cuh", os.path.join("..", "..", "include", "gst_cuda.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared", "-x", "cu",
