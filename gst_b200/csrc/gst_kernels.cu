@@ -114,9 +114,11 @@ __device__ __forceinline__ uint32_t pack16(int a, int b) {
 // The renorm words are staged through a per-warp, 1 KiB-aligned shared-memory ring filled with
 // cp.async in 256-byte, 256-byte-aligned chunks (group ranges are only 4-byte aligned, so the
 // windows are aligned down in absolute address space and the ring is indexed by the low
-// address bits).  A checkpoint every 4 symbols tops the ring up; 4 symbols consume at most
-// 4*32*2 = 256 B and a refill is issued whenever fewer than 512 B are staged, so a chunk is
-// always complete one checkpoint before its first byte is needed.
+// address bits).  A checkpoint every 4 symbols (which consume at most 4*32*2 = 256 B) tops the
+// ring up whenever fewer than 768 B are staged and then waits until at most the two newest
+// cp.async groups are pending: a chunk has two checkpoint intervals to land, and because at
+// least 512 B are staged at every checkpoint, the 256 B the next four symbols can touch are
+// always complete.
 //
 // Per symbol and lane (ans/ans_decode.cl:38-65):
 //   e = table[state & 2047];  state = (state >> 11) * e.freq + e.bias          (bias = slot - cum)
@@ -126,9 +128,12 @@ __device__ __forceinline__ uint32_t pack16(int a, int b) {
 // the state update is predicated.
 constexpr int kRing = 1024;
 constexpr int kChunk = 256;
-constexpr int kRunStride = 264;                    // one lane's 256 symbols + 8 B pad (66 words:
-                                                   // conflict-free 8-byte stores across lanes)
-constexpr int kStagePlane = kLanes * kRunStride;   // 8448 B: one decoded group
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 // emit(m, lo, hi): called 32 times; the 8 symbols at positions q0 = 248 - 8m .. q0 + 7 of this
 // lane's 256-symbol run, little-endian packed (lo = q0..q0+3, hi = q0+4..q0+7).
@@ -152,18 +157,19 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
   // ans/ans_decode.cl:31
   uint32_t state = active ? __ldg(reinterpret_cast<const uint32_t *>(a_pos) + lane) : 0u;
 
-  // preload [c_top - 768, c_top), c_top = a_pos rounded up to 256
+  // preload [c_top - 1024, c_top), c_top = a_pos rounded up to 256
   const uintptr_t lo16 = (reinterpret_cast<uintptr_t>(buf_lo) + 15) & ~static_cast<uintptr_t>(15);
   const uintptr_t hi16 = reinterpret_cast<uintptr_t>(buf_hi) & ~static_cast<uintptr_t>(15);
   const uintptr_t c_top = (a_pos + 255) & ~static_cast<uintptr_t>(255);
-  uintptr_t lo = c_top - 3 * kChunk;
-  {
-    uintptr_t a = lo + 16 * lane;
+  uintptr_t lo = c_top - 4 * kChunk;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uintptr_t a = lo + 16 * lane + 512 * i;
     if (a >= lo16 && a + 16 <= hi16) cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
-    a += 512;
-    if (lane < 16 && a >= lo16 && a + 16 <= hi16)
-      cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
   }
+  cp_async_commit();
+  cp_async_wait_group<0>();
+  __syncwarp();
 
   uint32_t cur2 = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
 
@@ -172,15 +178,16 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
     uint32_t acc[2] = {0u, 0u};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      // checkpoint: everything issued so far has landed; top up when < 512 B are staged
-      cp_async_wait_all();
-      __syncwarp();
-      if (cur2 - static_cast<uint32_t>(lo) < 510u) {
+      // checkpoint: top up when < 768 B are staged, then let the two newest groups fly
+      if (cur2 + 2u - static_cast<uint32_t>(lo) < 768u) {
         lo -= kChunk;
         const uintptr_t a = lo + 16 * lane;
         if (lane < 16 && a >= lo16 && a + 16 <= hi16)
           cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
       }
+      cp_async_commit();
+      cp_async_wait_group<2>();
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         uint32_t slot_a;  // tab_s + 4 * (state & 2047): one LOP3 + one IMAD
@@ -198,7 +205,7 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
     }
     emit(m, acc[0], acc[1]);
   }
-  cp_async_wait_all();
+  cp_async_wait_group<0>();
 }
 
 __device__ __forceinline__ void trap_unless_aligned(uint32_t s, uint32_t align) {
@@ -453,23 +460,26 @@ __device__ __forceinline__ void inverse_lift(int (&v)[LEN]) {
   for (int i = 0; i < LEN; ++i) v[i] = o[i];
 }
 
-// Work tiles (int16, per warp).  Intermediates are bounded by 128 + 672 per level (<= 3488
+// Work areas (int16, per warp).  Intermediates are bounded by 128 + 672 per level (<= 3488
 // after five levels) for ANY input bytes, so int16 storage is exact.
-//   Wlow: the 16x16 corners of two planes, 32 rows of 32 B; the two 16-byte chunks of row
-//         `rid` are swapped when (rid >> 2) & 1, which makes lane = row 16-byte accesses and
-//         lane = column 2-byte accesses conflict free without padding.
-//   W   : one 32x32 tile, 32 rows of 64 B, chunk j of row r stored at j ^ ((r >> 1) & 3).
-constexpr int kWBytes = 2048;
-constexpr int kWlowBytes = 1024;
-constexpr int kWarpWork = kWBytes + kWlowBytes;
+//   Wlow: the 16x16 corners of two tiles, 16 rows of 32 B each (tile A in the warp's X area,
+//         tile B in its Y area); the two 16-byte chunks of row r are swapped when (r >> 2) & 1,
+//         which makes lane = row 16-byte accesses and lane = column 2-byte accesses conflict
+//         free without padding.
+//   W   : one 32x32 tile, 32 rows of 64 B, chunk j of row r stored at j ^ ((r >> 1) & 3);
+//         rows 0..15 live in the X area, rows 16..31 overlay the tile's own 1 KiB of the
+//         symbol stage (its symbols are all in registers by then).
+constexpr int kXBytes = 1024;  // per warp: cp.async ring (phase 1) / Wlow tile A / W rows 0..15
+constexpr int kYBytes = 512;   // per warp: Wlow tile B
 
-// levels 2..16 on two planes at once: lanes 0-15 own plane A, lanes 16-31 plane B
+// levels 2..16 on two tiles at once: lanes 0-15 own tile A, lanes 16-31 tile B.
+// wl = this lane's Wlow area (X for lanes 0..15, Y for lanes 16..31).
 template <int LEN>
-__device__ __forceinline__ void low_level(uint32_t wl_s, uint32_t lane) {
+__device__ __forceinline__ void low_level(uint32_t wl, uint32_t lane) {
   const uint32_t rc = lane & 15;  // row in the row pass, column in the column pass
   // rows
   if (rc < LEN) {
-    const uint32_t row = wl_s + lane * 32 + (((lane >> 2) & 1) << 4);  // logical chunk 0
+    const uint32_t row = wl + rc * 32 + (((rc >> 2) & 1) << 4);  // logical chunk 0
     int v[LEN];
     if (LEN == 16) {
       const uint4 a = lds128(row), b = lds128(row ^ 16);
@@ -503,8 +513,7 @@ __device__ __forceinline__ void low_level(uint32_t wl_s, uint32_t lane) {
   __syncwarp();
   // columns
   if (rc < LEN) {
-    const uint32_t base = wl_s + (lane & 16) * 32;  // plane A or B
-    const uint32_t col[2] = {base + (((rc >> 3) ^ 0) << 4) + (rc & 7) * 2, base + (((rc >> 3) ^ 1) << 4) + (rc & 7) * 2};
+    const uint32_t col[2] = {wl + (((rc >> 3) ^ 0) << 4) + (rc & 7) * 2, wl + (((rc >> 3) ^ 1) << 4) + (rc & 7) * 2};
     int v[LEN];
 #pragma unroll
     for (int i = 0; i < LEN; ++i) v[i] = lds_s16(col[(i >> 2) & 1] + i * 32);
@@ -528,30 +537,52 @@ __device__ __forceinline__ uint32_t pack565(int y, int co, int cg) {  // low 16 
   return (static_cast<uint32_t>(r) << 11) | (static_cast<uint32_t>(g) << 5) | static_cast<uint32_t>(b);
 }
 
+// 4 sign-extended bytes of a word
+__device__ __forceinline__ void sext4(uint32_t w, int (&o)[4]) {
+  o[0] = sext_byte<0>(w); o[1] = sext_byte<1>(w); o[2] = sext_byte<2>(w); o[3] = sext_byte<3>(w);
+}
+
 // ---------------------------------------------------------------------------------------
 // The fused endpoint-plane kernel.  CTA (b, g) owns tiles [8g, 8g+8) of image b in all six
-// planes [Y1,Y2,Co1,Cg1,Co2,Cg2] (codec/assemble.cl:27-37) = one rANS group per plane.
-//   phase 1: warps 0..5 rANS-decode one group each into shared memory (48 KB of symbols)
-//   phase 2: warp t runs the 5-level inverse wavelet on tile t of every plane; levels 2..16 on
-//            two planes at a time (lane = plane x row / plane x column), level 32 per plane
-//            (lane = row in registers, then lane = column)
-//   phase 3: warp t assembles the 1024 DXT1 blocks (or RGB8 texels) of tile t with coalesced
-//            16-byte stores; the palette index is run_end - S (see side_streams_kernel).
-// Shared memory (1 KiB aligned): [6 rings][2 tables][2 KB] (phase 2 reuses these 24 KB as
-// 8 x (W + Wlow)) [6 staged groups].
-constexpr int kFusedWarps = 8;
-constexpr int kFusedAux = kFusedWarps * kWarpWork;  // 24576
-static_assert(kFusedAux >= 6 * kRing + 2 * kTableSize * 4, "phase 1 buffers must fit the aliased region");
-constexpr int kFusedSmem = kFusedAux + 6 * kStagePlane;  // 75264 B -> 3 CTAs / SM
+// planes [Y1,Y2,Co1,Cg1,Co2,Cg2] (codec/assemble.cl:27-37) = one rANS group per plane, and
+// WARP w OWNS PLANE w through phases 1 and 2, so the only CTA-wide barrier of the data path is
+// the one in front of the assembly:
+//   phase 1: the warp rANS-decodes the group of its plane into its 8 KiB symbol stage
+//   phase 2: the warp runs the 5-level inverse wavelet on the 8 tiles of that group; levels
+//            2..16 on two tiles at a time (lane = tile x row / tile x column), level 32 per tile
+//            (lane = row in registers, then lane = column); the int8 result replaces the
+//            tile's symbols in the stage, row-major
+//   phase 3: the six warps share the 64 four-row slabs of the 8 tiles: 4 DXT1 blocks (or 64
+//            RGB8 texels) per lane and slab, coalesced 16-byte stores; the palette index is
+//            run_end - S (see side_streams_kernel) and its loads run one slab ahead.
+//
+// Symbol stage: lane l of the rANS warp owns run l = bytes [256 l, 256 l + 256) of the group
+// (ans/ans_decode.cl:71); 8-byte chunk c of run r is stored at chunk position c ^ (r & 15) of
+// that run, which keeps the lane-strided 8-byte stores of phase 1 bank-conflict free without
+// padding.  Tile t = runs 4t..4t+3 = stage bytes [1024 t, 1024 t + 1024), row-major 32x32.
+//
+// Shared memory (1 KiB aligned): [6 X areas][2 tables][6 Y areas][6 stages] = 74752 B, three
+// CTAs (18 warps) per SM.
+constexpr int kFusedWarps = 6;
+constexpr int kStageBytes = kGroupSyms;                                   // 8192
+constexpr int kFusedTabOff = kFusedWarps * kXBytes;                      // 6144
+constexpr int kFusedYOff = kFusedTabOff + 2 * kTableSize * 4;            // 22528
+constexpr int kFusedStageOff = kFusedYOff + kFusedWarps * kYBytes;       // 25600
+constexpr int kFusedSmem = kFusedStageOff + kFusedWarps * kStageBytes;   // 74752
+static_assert(kXBytes == kRing, "the X area doubles as the cp.async ring");
+static_assert(kFusedStageOff % 1024 == 0, "tile slots must be 16-byte aligned");
 
 template <int RGB>
 __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const BatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_s = smem_u32(smem);
   trap_unless_aligned(smem_s, kRing);
-  const uint32_t stage_s = smem_s + kFusedAux;
-  const uint32_t tabs_s = smem_s + 6 * kRing;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tabs_s = smem_s + kFusedTabOff;
+  const uint32_t x_s = smem_s + warp * kXBytes;
+  const uint32_t y_s = smem_s + kFusedYOff + warp * kYBytes;
+  const uint32_t stage0_s = smem_s + kFusedStageOff;
+  const uint32_t stage_s = stage0_s + warp * kStageBytes;  // this warp's plane
   const uint32_t b = blockIdx.x / p.groups_per_plane;
   const uint32_t g = blockIdx.x % p.groups_per_plane;
   const ImageStreams is = image_streams(p, b);
@@ -561,74 +592,70 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
   load_table(tabs_s + kTableSize * 4, p.tables + (4ull * b + 1) * kTableSize, threadIdx.x, kFusedWarps * 32);
   __syncthreads();
 
-  if (warp < 6) {
-    // Y stream = Y1 || Y2, chroma stream = Co1 || Cg1 || Co2 || Cg2 (codec/encoder.cpp:87,93-95)
-    const bool chroma = warp >= 2;
-    const uint32_t group = (chroma ? warp - 2 : warp) * p.groups_per_plane + g;
-    const uint32_t my_stage = stage_s + warp * kStagePlane + lane * kRunStride + 248;
+  // ---- phase 1: rANS, warp = plane ------------------------------------------------------
+  // Y stream = Y1 || Y2, chroma stream = Co1 || Cg1 || Co2 || Cg2 (codec/encoder.cpp:87,93-95)
+  const bool chroma = warp >= 2;
+  const uint32_t group = (chroma ? warp - 2 : warp) * p.groups_per_plane + g;
+  {
+    const uint32_t run_s = stage_s + lane * 256;
+    const uint32_t sw = lane & 15;
     rans_decode_group<true>(tabs_s + (chroma ? kTableSize * 4 : 0), is.payload + (chroma ? is.in_off[1] : is.in_off[0]),
-                            group, kLanes, smem_s + warp * kRing, p.cmp, p.cmp + p.cmp_bytes,
-                            [&](int m, uint32_t lo, uint32_t hi) { sts64(my_stage - 8 * m, lo, hi); });
+                            group, kLanes, x_s, p.cmp, p.cmp + p.cmp_bytes,
+                            [&](int m, uint32_t lo, uint32_t hi) { sts64(run_s + (((31 - m) ^ sw) << 3), lo, hi); });
   }
-  __syncthreads();
+  __syncwarp();
 
   if (p.tap_symbols) {
-    for (uint32_t pl = 0; pl < 6; ++pl) {
-      const uint32_t group = (pl < 2 ? pl : pl - 2) * p.groups_per_plane + g;
-      uint8_t *dst = p.tap_symbols + (pl < 2 ? is.out_off[0] : is.out_off[1]) + static_cast<size_t>(group) * kGroupSyms;
-      for (uint32_t r = warp; r < kLanes; r += kFusedWarps) {
-        const uint2 v = lds64(stage_s + pl * kStagePlane + r * kRunStride + lane * 8);
-        *reinterpret_cast<uint2 *>(dst + r * 256 + lane * 8) = v;
-      }
+    uint8_t *dst = p.tap_symbols + (chroma ? is.out_off[1] : is.out_off[0]) + static_cast<size_t>(group) * kGroupSyms;
+    for (uint32_t r = 0; r < kLanes; ++r) {
+      const uint2 v = lds64(stage_s + r * 256 + ((lane ^ (r & 15)) << 3));
+      *reinterpret_cast<uint2 *>(dst + r * 256 + lane * 8) = v;
     }
-    __syncthreads();
+    __syncwarp();
   }
 
-  // ---- phase 2: inverse wavelet, warp = tile position --------------------------------
+  // ---- phase 2: inverse wavelet of the 8 tiles of this plane -------------------------------
   const uint32_t tiles_x = p.blocks_x / kTile;
-  const uint32_t tile = g * 8 + warp;
-  const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
-  const uint32_t w_s = smem_s + warp * kWarpWork;
-  const uint32_t wl_s = w_s + kWBytes;
-  const uint32_t tile_s = stage_s + 4 * warp * kRunStride;  // + plane * kStagePlane
-  // byte offset of row `lane` (row pass) / of rows 0..15 of the plane pair (corner load)
-  const uint32_t row_off = (lane >> 3) * kRunStride + (lane & 7) * 32;
+  const uint32_t tile0 = g * 8;
+  const uint32_t ty0 = tile0 / tiles_x, tx0 = tile0 % tiles_x;
+  const uint32_t wl = (lane & 16) ? y_s : x_s;  // this lane's Wlow area in the low levels
 
 #pragma unroll 1
-  for (uint32_t pair = 0; pair < 3; ++pair) {
-    // corners: lane -> (plane pair*2 + lane/16, row lane%16), bytes -> (byte - 128) as int16
+  for (uint32_t pair = 0; pair < 4; ++pair) {
+    // corners: lane -> (tile 2 pair + lane/16, row lane%16), bytes -> (byte - 128) as int16
     {
-      const uint32_t r = lane & 15;
-      const uint32_t src = tile_s + (2 * pair + (lane >> 4)) * kStagePlane + (r >> 3) * kRunStride + (r & 7) * 32;
-      const uint2 a = lds64(src), c = lds64(src + 8);
+      const uint32_t t = 2 * pair + (lane >> 4), r = lane & 15;
+      // row r of tile t: run 4t + r/8, chunks 4 (r%8) + j; chunk position = chunk ^ (run & 15)
+      const uint32_t a0 = stage_s + (4 * t + (r >> 3)) * 256 + ((4 * ((r & 7) ^ (t & 3)) + (r >> 3)) << 3);
+      const uint2 a = lds64(a0), c = lds64(a0 ^ 8);
       const uint32_t x0 = a.x ^ 0x80808080u, x1 = a.y ^ 0x80808080u, x2 = c.x ^ 0x80808080u, x3 = c.y ^ 0x80808080u;
-      const uint32_t row = wl_s + lane * 32 + (((lane >> 2) & 1) << 4);
+      const uint32_t row = wl + r * 32 + (((r >> 2) & 1) << 4);
       sts128(row, sext_byte_pair<0>(x0), sext_byte_pair<2>(x0), sext_byte_pair<0>(x1), sext_byte_pair<2>(x1));
       sts128(row ^ 16, sext_byte_pair<0>(x2), sext_byte_pair<2>(x2), sext_byte_pair<0>(x3), sext_byte_pair<2>(x3));
     }
     __syncwarp();
-    low_level<2>(wl_s, lane);
-    low_level<4>(wl_s, lane);
-    low_level<8>(wl_s, lane);
-    low_level<16>(wl_s, lane);
+    low_level<2>(wl, lane);
+    low_level<4>(wl, lane);
+    low_level<8>(wl, lane);
+    low_level<16>(wl, lane);
 
 #pragma unroll 1
     for (uint32_t q = 0; q < 2; ++q) {
-      const uint32_t pl = 2 * pair + q;
-      const uint32_t ts = tile_s + pl * kStagePlane;
+      const uint32_t t = 2 * pair + q;
+      const uint32_t slot = stage_s + t * kTileSyms;  // this tile's 1 KiB of the stage
       // ---- level 32, rows: lane = row
       {
         int v[32];
-        const uint32_t src = ts + row_off;
+        // symbol chunks j = 0..3 of row `lane` sit at sym0 ^ (8 j)
+        const uint32_t sym0 = slot + (lane >> 3) * 256 + ((4 * ((lane & 7) ^ (t & 3)) + (lane >> 3)) << 3);
         if (lane < 16) {  // low half of rows 0..15 = the 16x16 result of the lower levels
-          const uint32_t rid = q * 16 + lane;
-          const uint32_t row = wl_s + rid * 32 + (((rid >> 2) & 1) << 4);
+          const uint32_t row = (q ? y_s : x_s) + lane * 32 + (((lane >> 2) & 1) << 4);
           const uint4 a = lds128(row), c = lds128(row ^ 16);
           const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
         } else {
-          const uint2 a = lds64(src), c = lds64(src + 8);
+          const uint2 a = lds64(sym0), c = lds64(sym0 ^ 8);
           const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, c.x ^ 0x80808080u, c.y ^ 0x80808080u};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -637,7 +664,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
           }
         }
         {
-          const uint2 a = lds64(src + 16), c = lds64(src + 24);
+          const uint2 a = lds64(sym0 ^ 16), c = lds64(sym0 ^ 24);
           const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, c.x ^ 0x80808080u, c.y ^ 0x80808080u};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -645,8 +672,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
             v[16 + 4 * i + 2] = sext_byte<2>(x[i]); v[16 + 4 * i + 3] = sext_byte<3>(x[i]);
           }
         }
+        __syncwarp();  // every lane holds its row: the tile's symbols and Wlow may be overwritten
         inverse_lift<32>(v);
-        const uint32_t wrow = w_s + lane * 64 + (((lane >> 1) & 3) << 4);  // logical chunk 0
+        const uint32_t wrow = (lane < 16 ? x_s + lane * 64 : slot + (lane - 16) * 64) + (((lane >> 1) & 3) << 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           sts128(wrow ^ (j << 4), pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
@@ -654,19 +682,26 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
       }
       __syncwarp();
       // ---- level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
-      // back into the staging slot of this tile as row-major bytes
+      // back into the tile's slot as row-major bytes
       {
-        uint32_t col[4];
+        uint32_t colx[4], cols[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) col[s] = w_s + ((((lane >> 3) ^ s) & 3) << 4) + (lane & 7) * 2;
+        for (int s = 0; s < 4; ++s) {
+          const uint32_t o = ((((lane >> 3) ^ s) & 3) << 4) + (lane & 7) * 2;
+          colx[s] = x_s + o;
+          cols[s] = slot + o - 16 * 64;
+        }
         int v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lds_s16(col[(i >> 1) & 3] + i * 64);
+        for (int i = 0; i < 32; ++i) v[i] = lds_s16((i < 16 ? colx[(i >> 1) & 3] : cols[(i >> 1) & 3]) + i * 64);
+        __syncwarp();  // W is in registers: the slot may take the result
         inverse_lift<32>(v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sts8(ts + (i >> 3) * kRunStride + (i & 7) * 32 + lane, static_cast<uint32_t>(v[i]));
+        for (int i = 0; i < 32; ++i) sts8(slot + i * 32 + lane, static_cast<uint32_t>(v[i]));
         if (p.tap_planes) {
-          int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + pl) * p.n_blocks +
+          uint32_t tx = tx0 + t, ty = ty0;
+          while (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+          int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + warp) * p.n_blocks +
                        static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
 #pragma unroll
           for (int i = 0; i < 32; ++i) tp[static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i]);
@@ -675,25 +710,26 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
       __syncwarp();
     }
   }
+  __syncthreads();
 
   // ---- phase 3: assembly, codec/assemble.cl:64-129 -------------------------------------
   const uint32_t n_entries = is.palette_bytes / 4;
   const bool pal_ok = static_cast<uint64_t>(is.pal_off) + is.palette_bytes <= p.palette_cap && n_entries > 0;
   const uint32_t *pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? is.pal_off : 0));
   const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
-  const uint32_t tile_block0 = ty * kTile * p.blocks_x + tx * kTile;
   const int32_t *run_end = p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane);
   const bool idx16 = p.idx16 != 0;
+  const uint32_t lane_row = lane >> 3, lane_col = 4 * (lane & 7);
 
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t row = 4 * k + (lane >> 3), col = 4 * (lane & 7);
-    const uint32_t gidx = tile_block0 + row * p.blocks_x + col;
-    const uint32_t slot = tile_s + (row >> 3) * kRunStride + (row & 7) * 32 + col;
-    uint32_t pw[6];
-#pragma unroll
-    for (int pl = 0; pl < 6; ++pl) pw[pl] = lds32(slot + pl * kStagePlane);
-    uint32_t sfx[4];
+  // slab u = 8 * tile + k: rows 4k..4k+3 of tile (g * 8 + u / 8); first block of this lane
+  auto slab_gidx = [&](uint32_t u) -> uint32_t {
+    uint32_t tx = tx0 + (u >> 3), ty = ty0;
+    while (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    return (ty * kTile + 4 * (u & 7) + lane_row) * p.blocks_x + tx * kTile + lane_col;
+  };
+  // stage A: suffix sums + run end of the 4 blocks;  stage B: indices -> palette words
+  uint32_t sfx[4] = {0u, 0u, 0u, 0u}, re = 0u, word_nx[4] = {0u, 0u, 0u, 0u};
+  auto load_sfx = [&](uint32_t gidx) {
     if (idx16) {
       const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(p.idx_s) + img_block0 + gidx));
       sfx[0] = sv.x & 0xFFFFu; sfx[1] = sv.x >> 16; sfx[2] = sv.y & 0xFFFFu; sfx[3] = sv.y >> 16;
@@ -701,24 +737,44 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
       const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + img_block0 + gidx));
       sfx[0] = sv.x; sfx[1] = sv.y; sfx[2] = sv.z; sfx[3] = sv.w;
     }
-    const uint32_t re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
-    uint32_t idx[4], word[4];
+    re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
+  };
+  auto load_words = [&](uint32_t gidx) {
+    uint32_t idx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       idx[j] = re - sfx[j];
       if (idx16) idx[j] &= 0xFFFFu;
-      word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
+      word_nx[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
     }
     if (p.tap_indices)
       *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
+  };
+
+  uint32_t gidx_b = slab_gidx(warp);  // gidx of the slab whose words are being loaded
+  load_sfx(gidx_b);
+  load_words(gidx_b);
+  if (warp + kFusedWarps < 64) {
+    gidx_b = slab_gidx(warp + kFusedWarps);
+    load_sfx(gidx_b);
+  }
+
+#pragma unroll 1
+  for (uint32_t u = warp; u < 64; u += kFusedWarps) {
+    const uint32_t gidx = slab_gidx(u);
+    uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
+    if (u + kFusedWarps < 64) load_words(gidx_b);  // sfx / re of slab u + 6 arrived during slab u - 6
+    if (u + 2 * kFusedWarps < 64) {
+      gidx_b = slab_gidx(u + 2 * kFusedWarps);
+      load_sfx(gidx_b);
+    }
+    const uint32_t src = stage0_s + u * 128 + lane * 4;  // rows 4k..4k+3 of the tile, 4 bytes per lane
+    uint32_t pw[6];
+#pragma unroll
+    for (int pl = 0; pl < 6; ++pl) pw[pl] = lds32(src + pl * kStageBytes);
 
     int y1[4], y2[4], co1[4], cg1[4], co2[4], cg2[4];
-    y1[0] = sext_byte<0>(pw[0]); y1[1] = sext_byte<1>(pw[0]); y1[2] = sext_byte<2>(pw[0]); y1[3] = sext_byte<3>(pw[0]);
-    y2[0] = sext_byte<0>(pw[1]); y2[1] = sext_byte<1>(pw[1]); y2[2] = sext_byte<2>(pw[1]); y2[3] = sext_byte<3>(pw[1]);
-    co1[0] = sext_byte<0>(pw[2]); co1[1] = sext_byte<1>(pw[2]); co1[2] = sext_byte<2>(pw[2]); co1[3] = sext_byte<3>(pw[2]);
-    cg1[0] = sext_byte<0>(pw[3]); cg1[1] = sext_byte<1>(pw[3]); cg1[2] = sext_byte<2>(pw[3]); cg1[3] = sext_byte<3>(pw[3]);
-    co2[0] = sext_byte<0>(pw[4]); co2[1] = sext_byte<1>(pw[4]); co2[2] = sext_byte<2>(pw[4]); co2[3] = sext_byte<3>(pw[4]);
-    cg2[0] = sext_byte<0>(pw[5]); cg2[1] = sext_byte<1>(pw[5]); cg2[2] = sext_byte<2>(pw[5]); cg2[3] = sext_byte<3>(pw[5]);
+    sext4(pw[0], y1); sext4(pw[1], y2); sext4(pw[2], co1); sext4(pw[3], cg1); sext4(pw[4], co2); sext4(pw[5], cg2);
 
     if (!RGB) {
       uint32_t o[8];
@@ -757,9 +813,11 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
 #pragma unroll
         for (int s = 0; s < 4; ++s) pal4[j][s] = e[s];
       }
+      // texel coordinates of this lane's first block
       const size_t img_w = 4ull * p.blocks_x;
       uint8_t *img = p.out + static_cast<size_t>(b) * p.n_blocks * 48;
-      const size_t x0 = 4ull * (tx * kTile + col), y0 = 4ull * (ty * kTile + row);
+      const uint32_t by = gidx / p.blocks_x, bx = gidx - by * p.blocks_x;
+      const size_t x0 = 4ull * bx, y0 = 4ull * by;
 #pragma unroll
       for (int yy = 0; yy < 4; ++yy) {
         uint32_t t[16];  // 16 texels of this texel row, r | g << 8 | b << 16
