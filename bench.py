@@ -344,11 +344,14 @@ def main():
         except Exception:
             pass
         peak, peak_src = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        # dominant kernel: fused_planes (Y + chroma rANS, wavelet, assembly).  Its algorithmic
-        # bytes: the Y and chroma streams + their two 512-byte freq tables read once, the DXT1
-        # blocks written once.
-        fused_bytes = float(sum(h.y_cmp_sz + h.chroma_cmp_sz + 1024 for h in hdrs)) + 8.0 * N * images
-        fused_ms = kernel_ms["fused_planes"] / max(calls, 1)
+        # Algorithmic bytes (compressed bytes read once + DXT1 bytes written once) split
+        # over the two heavy kernels: rans_streams reads every compressed stream and frequency table,
+        # wavelet_assemble writes every DXT1 block.  The transposed symbol scratch between them is
+        # an intermediate and not counted.  `roofline` describes whichever kernel takes longer.
+        per_call = {k: v / max(calls, 1) for k, v in kernel_ms.items()}
+        alg = {"rans_streams": cmp_rank, "wavelet_assemble": 8.0 * N * images}
+        dom = max(alg, key=lambda k: per_call.get(k, 0.0))
+        fused_bytes, fused_ms = alg[dom], per_call[dom]
         achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
         step_gbs = alg_bytes_rank / (ms_step * 1e-3) / 1e9
         line = {
@@ -364,11 +367,12 @@ def main():
                        "l2": "inputs+outputs per step exceed the 126 MB L2" if alg_bytes_rank > 2 * 126e6 else
                              "working set fits L2 (latency-bound config)",
                        "parity": f"{checked} distinct images + last checked bit-exact before timing"},
-            "roofline": {"bound": "hbm", "kernel": "fused_planes_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "kernel_ms": fused_ms, "kernel_bytes": fused_bytes,
                          "step_achieved": step_gbs, "step_frac": step_gbs / peak,
-                         "kernel_ms_all": {k: v / max(calls, 1) for k, v in kernel_ms.items()}},
+                         "kernel_ms_all": per_call,
+                         "kernel_alg_bytes": alg},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": lib().gst_launches_per_batch() * args.steps,
             "clocks": clocks,
         }

@@ -112,7 +112,7 @@ struct BatchLayout {
   uint32_t n_blocks = 0, groups_per_plane = 0, max_palette = 0;
   size_t off_region = 0, payload_bytes = 0, palette_total = 0, total_cmp = 0;
   // scratch carve-up
-  size_t tables_off = 0, palette_off = 0, idx_off = 0, total_off = 0, run_off = 0, scratch_bytes = 0;
+  size_t tables_off = 0, sym_off = 0, palette_off = 0, idx_off = 0, total_off = 0, run_off = 0, scratch_bytes = 0;
   bool idx16 = true;
 };
 
@@ -145,6 +145,7 @@ int layout_batch(const gst_header *hdrs, uint32_t n, BatchLayout *L) {
   L->total_cmp = L->off_region + static_cast<size_t>(n) * 2048 + L->payload_bytes;
   size_t off = 0;
   L->tables_off = off;  off += align_up(static_cast<size_t>(n) * 4 * gst::kTableSize * 4, kQuantum);
+  L->sym_off = off;     off += align_up(static_cast<size_t>(n) * 6 * N, kQuantum);
   L->palette_off = off; off += align_up(std::max<size_t>(L->palette_total, 16), kQuantum);
   // palette indices < 2^16 everywhere -> the per-block index suffix sums are kept as u16
   L->idx16 = max_pal / 4 <= 65536u;
@@ -199,6 +200,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.off_region = static_cast<uint32_t>(L.off_region);
   p.groups_per_plane = L.groups_per_plane;
   p.tables = reinterpret_cast<uint32_t *>(scratch + L.tables_off);
+  p.sym_t = scratch + L.sym_off;
   p.palette = scratch + L.palette_off;
   p.palette_cap = L.palette_total;
   p.idx_s = scratch + L.idx_off;

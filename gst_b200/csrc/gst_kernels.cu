@@ -1,17 +1,19 @@
 // gst_b200 -- sm_100a kernels for the .gst -> DXT1 decode path.
 //
 // Kernel inventory (reference stage it replaces, citations relative to the reference tree):
-//   build_tables_kernel   stage 1  ans/build_table.cl:12-83
-//   side_streams_kernel   stage 2 for the palette + index streams, with stage 3
-//                         (codec/decode_indices.cl:6-84, host loop codec/decoder.cpp:311-393)
-//                         fused behind the rANS warp as a group-local prefix sum
-//   index_carry_kernel    the cross-group part of stage 3 (exclusive scan of group totals)
-//   fused_planes_kernel   stage 2 for the six endpoint planes (ans/ans_decode.cl:25-143),
-//                         stage 4 (codec/inverse_wavelet.cl:69-192) and stage 5
-//                         (codec/assemble.cl:64-129) in one CTA; the symbol bytes and the
-//                         wavelet planes never leave shared memory
+//   build_tables_kernel      stage 1  ans/build_table.cl:12-83
+//   rans_streams_kernel      stage 2  ans/ans_decode.cl:25-143 for all four streams of every image,
+//                            one warp per 32-stream group at full occupancy.  Plane symbols go to
+//                            an L2-friendly transposed scratch, palette symbols to the compact
+//                            palette, and for the index stream stage 3 (codec/decode_indices.cl:6-84,
+//                            host loop codec/decoder.cpp:311-393) is fused behind the rANS warp as a
+//                            group-local suffix sum
+//   index_carry_kernel       the cross-group part of stage 3 (exclusive scan of group totals)
+//   wavelet_assemble_kernel  stage 4 (codec/inverse_wavelet.cl:69-192) and stage 5
+//                            (codec/assemble.cl:64-129): one warp per 32x32 tile, all six planes;
+//                            the wavelet planes never leave shared memory
 //   ans_decode_plain_kernel  the standalone `ans_decode` entry (ans/ans_decode.cl:76-95),
-//                         1..32 interleaved lanes, used by the OpenCLDecoder-style API
+//                            1..32 interleaved lanes, used by the OpenCLDecoder-style API
 //
 // All arithmetic is integer and follows the reference bit for bit: wrapping u32 rANS
 // state, C truncating division in the 5/3 lifting and in YCoCg->RGB, (char) truncation of
@@ -135,8 +137,8 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// emit(m, lo, hi): called 32 times; the 8 symbols at positions q0 = 248 - 8m .. q0 + 7 of this
-// lane's 256-symbol run, little-endian packed (lo = q0..q0+3, hi = q0+4..q0+7).
+// emit(m, w0, w1, w2, w3): called 16 times; the 16 symbols at positions q0 = 240 - 16m .. q0 + 15
+// of this lane's 256-symbol run, little-endian packed (w0 = q0..q0+3, ..., w3 = q0+12..q0+15).
 template <bool FULL, class Emit>
 __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t *__restrict__ stream,
                                                   uint32_t group, uint32_t n_lanes, uint32_t ring_s,
@@ -174,10 +176,10 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
   uint32_t cur2 = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
 
 #pragma unroll 1
-  for (int m = 0; m < 32; ++m) {
-    uint32_t acc[2] = {0u, 0u};
+  for (int m = 0; m < 16; ++m) {
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
       // checkpoint: top up when < 768 B are staged, then let the two newest groups fly
       if (cur2 + 2u - static_cast<uint32_t>(lo) < 768u) {
         lo -= kChunk;
@@ -200,10 +202,10 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
         const uint32_t w = lds_u16(ring_s | (a & (kRing - 1)));
         if (need) state = __byte_perm(w, state, 0x5410);  // state << 16 | w
         cur2 -= 2u * __popc(mask);                        // ans/ans_decode.cl:65
-        acc[1 - h] = __byte_perm(acc[1 - h], e, 0x2104);  // acc << 8 | symbol
+        acc[3 - h] = __byte_perm(acc[3 - h], e, 0x2104);  // acc << 8 | symbol
       }
     }
-    emit(m, acc[0], acc[1]);
+    emit(m, acc[0], acc[1], acc[2], acc[3]);
   }
   cp_async_wait_group<0>();
 }
@@ -307,86 +309,120 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 }
 
 // ---------------------------------------------------------------------------------------
-// Palette + index streams.  One warp per rANS group, 8 warps per CTA, all warps of a CTA on
-// the same stream (one table in shared memory); no symbol staging, so 6 CTAs fit an SM.
+// Stage 2 for every stream of every image.  One warp per rANS group, 8 warps per CTA, all warps
+// of a CTA on the same stream of the same image (one 8 KiB table in shared memory); 16 KiB of
+// shared memory and <= 32 registers per thread, so an SM holds 64 warps = 64 independent rANS
+// chains -- the decode loop is a chain of dependent shared-memory lookups (~200 cycles per
+// symbol), and only this many chains keep the issue slots busy.
+//
+//   Y / chroma groups: the symbols are the wavelet coefficients of the six endpoint planes
+//       (Y = Y1 || Y2, chroma = Co1 || Cg1 || Co2 || Cg2, codec/encoder.cpp:87,93-95), one group =
+//       8 tiles of one plane.  They go to the transposed scratch sym_t: image b, plane-group
+//       pg = plane * groups_per_plane + g holds [k = 0..15][lane = 0..31][16 B], where the 16
+//       bytes are positions 16k..16k+15 of the lane's run.  One warp store is 512 contiguous
+//       bytes (the reference layout would be 32 pieces 256 B apart); wavelet_assemble_kernel
+//       reads 16-byte pieces, which is all it needs.
 //   palette groups: symbols go straight to the compact palette scratch (they are the u32 DXT
-//                   index words, codec/encoder.cpp:100-108)
-//   index groups:   symbols are (delta + 128) per DXT block in raster order
-//                   (codec/dxt_image.cpp:610-618) and every lane owns 256 consecutive blocks
-//                   (a "run").  Stage 3 (codec/decode_indices.cl:24, idx[i] = sum_{j<=i} d[j])
-//                   is fused behind the decoder: symbols arrive last-to-first, so the lane
-//                   writes S[i] = sum of the deltas AFTER i inside its run, and
-//                   idx[i] = run_end[run] - S[i], where run_end is the inclusive prefix at the
-//                   end of the run (finished by index_carry_kernel).  S is stored mod 2^16 when
-//                   every palette of the batch has <= 65536 entries (idx < 2^16 then makes the
-//                   16-bit difference exact), else as 32 bits.
-constexpr int kSideWarps = 8;
-constexpr int kSideSmem = kSideWarps * kRing + kTableSize * 4;
+//       index words, codec/encoder.cpp:100-108)
+//   index groups: symbols are (delta + 128) per DXT block in raster order
+//       (codec/dxt_image.cpp:610-618) and every lane owns 256 consecutive blocks (a "run").
+//       Stage 3 (codec/decode_indices.cl:24, idx[i] = sum_{j<=i} d[j]) is fused behind the
+//       decoder: symbols arrive last-to-first, so the lane writes S[i] = sum of the deltas AFTER
+//       i inside its run, and idx[i] = run_end[run] - S[i], where run_end is the inclusive
+//       prefix at the end of the run (finished by index_carry_kernel).  S is stored mod 2^16
+//       when every palette of the batch has <= 65536 entries (idx < 2^16 then makes the 16-bit
+//       difference exact), else as 32 bits, in the same transposed order as sym_t:
+//       [group][k][lane][16 values].
+constexpr int kRansWarps = 8;
+constexpr int kRansSmem = kRansWarps * kRing + kTableSize * 4;
 
-__global__ void __launch_bounds__(kSideWarps * 32, 6)
-    side_streams_kernel(const BatchParams p, uint32_t pal_ctas, uint32_t idx_ctas) {
+// CTAs of one image: [Y][chroma][palette][index]
+struct StreamGrid {
+  uint32_t y_ctas, c_ctas, pal_ctas, idx_ctas;
+  __host__ __device__ uint32_t per_image() const { return y_ctas + c_ctas + pal_ctas + idx_ctas; }
+};
+
+__global__ void __launch_bounds__(kRansWarps * 32, 8) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_s = smem_u32(smem);
   trap_unless_aligned(smem_s, kRing);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring_s = smem_s + warp * kRing;
-  const uint32_t tab_s = smem_s + kSideWarps * kRing;
+  const uint32_t tab_s = smem_s + kRansWarps * kRing;
 
-  const uint32_t per_image = pal_ctas + idx_ctas;
+  const uint32_t per_image = sg.per_image();
   const uint32_t b = blockIdx.x / per_image;
-  const uint32_t r = blockIdx.x % per_image;
-  const bool is_index = r >= pal_ctas;
-  const uint32_t type = is_index ? 3u : 2u;
+  uint32_t r = blockIdx.x % per_image;
+  uint32_t type;  // 0 Y, 1 chroma, 2 palette, 3 index
+  if (r < sg.y_ctas) type = 0;
+  else if ((r -= sg.y_ctas) < sg.c_ctas) type = 1;
+  else if ((r -= sg.c_ctas) < sg.pal_ctas) type = 2;
+  else { r -= sg.pal_ctas; type = 3; }
   const ImageStreams is = image_streams(p, b);
-  const uint32_t n_groups = is_index ? p.groups_per_plane : is.palette_bytes / kGroupSyms;
-  const uint32_t first = (is_index ? r - pal_ctas : r) * kSideWarps;
+  const uint32_t n_groups = type == 0 ? 2 * p.groups_per_plane : type == 1 ? 4 * p.groups_per_plane
+                          : type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
+  const uint32_t first = r * kRansWarps;
   if (first >= n_groups) return;
 
-  load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kSideWarps * 32);
+  load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
   __syncthreads();
   const uint32_t group = first + warp;
   if (group >= n_groups) return;
-  const uint8_t *stream = is.payload + (is_index ? is.in_off[3] : is.in_off[2]);
-  const uint32_t out_off = is_index ? is.out_off[3] : is.out_off[2];
-  uint8_t *tap = p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 248
+  // in_off[type] / out_off[type] by selection (a dynamically indexed array would live in local memory)
+  const uint32_t in_off = type == 0 ? is.in_off[0] : type == 1 ? is.in_off[1] : type == 2 ? is.in_off[2] : is.in_off[3];
+  const uint32_t out_off = type == 0 ? is.out_off[0] : type == 1 ? is.out_off[1] : type == 2 ? is.out_off[2] : is.out_off[3];
+  const uint8_t *stream = is.payload + in_off;
+  uint8_t *tap = p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 240
                                : nullptr;
 
-  if (!is_index) {
+  if (type < 2) {
+    const size_t pg = (type ? 2 * p.groups_per_plane : 0) + group;
+    uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + pg * kGroupSyms + 15 * 512 + lane * 16;
+    rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                            [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                              *reinterpret_cast<uint4 *>(dst - 512 * m) = make_uint4(w0, w1, w2, w3);
+                              if (tap) *reinterpret_cast<uint4 *>(tap - 16 * m) = make_uint4(w0, w1, w2, w3);
+                            });
+    return;
+  }
+  if (type == 2) {
     const uint64_t off = static_cast<uint64_t>(is.pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
     const bool ok = off + kGroupSyms <= p.palette_cap;
-    uint8_t *dst = p.palette + off + lane * kSymsPerLane + 248;
+    uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
     rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                            [&](int m, uint32_t lo, uint32_t hi) {
-                              if (ok) *reinterpret_cast<uint2 *>(dst - 8 * m) = make_uint2(lo, hi);
-                              if (tap) *reinterpret_cast<uint2 *>(tap - 8 * m) = make_uint2(lo, hi);
+                            [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                              if (ok) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w0, w1, w2, w3);
+                              if (tap) *reinterpret_cast<uint4 *>(tap - 16 * m) = make_uint4(w0, w1, w2, w3);
                             });
     return;
   }
 
   uint32_t sum = 0;  // sum of (byte - 128) over the symbols decoded so far = positions after the current one
-  const size_t run0 = static_cast<size_t>(b) * p.n_blocks + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 248;
-  uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + run0;
-  uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + run0;
+  const size_t t0 = static_cast<size_t>(b) * p.n_blocks + static_cast<size_t>(group) * kGroupSyms + 15 * 512 + lane * 16;
+  uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
+  uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
   const bool idx16 = p.idx16 != 0;
   rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                          [&](int m, uint32_t lo, uint32_t hi) {
-                            if (tap) *reinterpret_cast<uint2 *>(tap - 8 * m) = make_uint2(lo, hi);
-                            uint32_t s[8];
-                            s[7] = sum; sum += ((hi >> 24) & 0xFFu) - 128u;
-                            s[6] = sum; sum += ((hi >> 16) & 0xFFu) - 128u;
-                            s[5] = sum; sum += ((hi >> 8) & 0xFFu) - 128u;
-                            s[4] = sum; sum += (hi & 0xFFu) - 128u;
-                            s[3] = sum; sum += ((lo >> 24) & 0xFFu) - 128u;
-                            s[2] = sum; sum += ((lo >> 16) & 0xFFu) - 128u;
-                            s[1] = sum; sum += ((lo >> 8) & 0xFFu) - 128u;
-                            s[0] = sum; sum += (lo & 0xFFu) - 128u;
+                          [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                            if (tap) *reinterpret_cast<uint4 *>(tap - 16 * m) = make_uint4(w0, w1, w2, w3);
+                            const uint32_t w[4] = {w0, w1, w2, w3};
+                            uint32_t s[16];
+#pragma unroll
+                            for (int i = 15; i >= 0; --i) {
+                              s[i] = sum;
+                              sum += ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 128u;
+                            }
                             if (idx16) {
-                              *reinterpret_cast<uint4 *>(dst16 - 8 * m) =
-                                  make_uint4(__byte_perm(s[0], s[1], 0x5410), __byte_perm(s[2], s[3], 0x5410),
-                                             __byte_perm(s[4], s[5], 0x5410), __byte_perm(s[6], s[7], 0x5410));
+                              uint32_t q[8];
+#pragma unroll
+                              for (int i = 0; i < 8; ++i) q[i] = __byte_perm(s[2 * i], s[2 * i + 1], 0x5410);
+                              *reinterpret_cast<uint4 *>(dst16 - 512 * m) = make_uint4(q[0], q[1], q[2], q[3]);
+                              *reinterpret_cast<uint4 *>(dst16 - 512 * m + 8) = make_uint4(q[4], q[5], q[6], q[7]);
                             } else {
-                              *reinterpret_cast<uint4 *>(dst32 - 8 * m) = make_uint4(s[0], s[1], s[2], s[3]);
-                              *reinterpret_cast<uint4 *>(dst32 - 8 * m + 4) = make_uint4(s[4], s[5], s[6], s[7]);
+#pragma unroll
+                              for (int i = 0; i < 4; ++i)
+                                *reinterpret_cast<uint4 *>(dst32 - 512 * m + 4 * i) =
+                                    make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
                             }
                           });
   // group-local inclusive prefix at the end of every run, and the group total
@@ -462,18 +498,18 @@ __device__ __forceinline__ void inverse_lift(int (&v)[LEN]) {
 
 // Work areas (int16, per warp).  Intermediates are bounded by 128 + 672 per level (<= 3488
 // after five levels) for ANY input bytes, so int16 storage is exact.
-//   Wlow: the 16x16 corners of two tiles, 16 rows of 32 B each (tile A in the warp's X area,
-//         tile B in its Y area); the two 16-byte chunks of row r are swapped when (r >> 2) & 1,
-//         which makes lane = row 16-byte accesses and lane = column 2-byte accesses conflict
-//         free without padding.
-//   W   : one 32x32 tile, 32 rows of 64 B, chunk j of row r stored at j ^ ((r >> 1) & 3);
-//         rows 0..15 live in the X area, rows 16..31 overlay the tile's own 1 KiB of the
-//         symbol stage (its symbols are all in registers by then).
-constexpr int kXBytes = 1024;  // per warp: cp.async ring (phase 1) / Wlow tile A / W rows 0..15
-constexpr int kYBytes = 512;   // per warp: Wlow tile B
+//   Wlow: the 16x16 corners of two planes, 2 x 16 rows of 32 B; the two 16-byte chunks of
+//         row r are swapped when (r >> 2) & 1, which makes lane = row 16-byte accesses and
+//         lane = column 2-byte accesses conflict free without padding.
+//   W   : one 32x32 tile, 32 rows of 64 B, chunk j of row r stored at j ^ ((r >> 1) & 3).
+//   res : the six int8 result planes of the tile, row-major 32x32, read by the assembly.
+constexpr int kWBytes = 2048;
+constexpr int kWlowBytes = 1024;
+constexpr int kResBytes = 6 * kTileSyms;
+constexpr int kWarpWork = kWBytes + kWlowBytes + kResBytes;  // 9216
 
-// levels 2..16 on two tiles at once: lanes 0-15 own tile A, lanes 16-31 tile B.
-// wl = this lane's Wlow area (X for lanes 0..15, Y for lanes 16..31).
+// levels 2..16 on two planes at once: lanes 0-15 own plane A, lanes 16-31 plane B.
+// wl = this lane's 512-byte half of Wlow.
 template <int LEN>
 __device__ __forceinline__ void low_level(uint32_t wl, uint32_t lane) {
   const uint32_t rc = lane & 15;  // row in the row pass, column in the column pass
@@ -543,198 +579,55 @@ __device__ __forceinline__ void sext4(uint32_t w, int (&o)[4]) {
 }
 
 // ---------------------------------------------------------------------------------------
-// The fused endpoint-plane kernel.  CTA (b, g) owns tiles [8g, 8g+8) of image b in all six
-// planes [Y1,Y2,Co1,Cg1,Co2,Cg2] (codec/assemble.cl:27-37) = one rANS group per plane, and
-// WARP w OWNS PLANE w through phases 1 and 2, so the only CTA-wide barrier of the data path is
-// the one in front of the assembly:
-//   phase 1: the warp rANS-decodes the group of its plane into its 8 KiB symbol stage
-//   phase 2: the warp runs the 5-level inverse wavelet on the 8 tiles of that group; levels
-//            2..16 on two tiles at a time (lane = tile x row / tile x column), level 32 per tile
-//            (lane = row in registers, then lane = column); the int8 result replaces the
-//            tile's symbols in the stage, row-major
-//   phase 3: the six warps share the 64 four-row slabs of the 8 tiles: 4 DXT1 blocks (or 64
-//            RGB8 texels) per lane and slab, coalesced 16-byte stores; the palette index is
-//            run_end - S (see side_streams_kernel) and its loads run one slab ahead.
-//
-// Symbol stage: lane l of the rANS warp owns run l = bytes [256 l, 256 l + 256) of the group
-// (ans/ans_decode.cl:71); 8-byte chunk c of run r is stored at chunk position c ^ (r & 15) of
-// that run, which keeps the lane-strided 8-byte stores of phase 1 bank-conflict free without
-// padding.  Tile t = runs 4t..4t+3 = stage bytes [1024 t, 1024 t + 1024), row-major 32x32.
-//
-// Shared memory (1 KiB aligned): [6 X areas][2 tables][6 Y areas][6 stages] = 74752 B, three
-// CTAs (18 warps) per SM.
-constexpr int kFusedWarps = 6;
-constexpr int kStageBytes = kGroupSyms;                                   // 8192
-constexpr int kFusedTabOff = kFusedWarps * kXBytes;                      // 6144
-constexpr int kFusedYOff = kFusedTabOff + 2 * kTableSize * 4;            // 22528
-constexpr int kFusedStageOff = kFusedYOff + kFusedWarps * kYBytes;       // 25600
-constexpr int kFusedSmem = kFusedStageOff + kFusedWarps * kStageBytes;   // 74752
-static_assert(kXBytes == kRing, "the X area doubles as the cp.async ring");
-static_assert(kFusedStageOff % 1024 == 0, "tile slots must be 16-byte aligned");
+// Stages 4 + 5.  One warp per 32x32 tile (1024 DXT blocks) of one image, through all six
+// planes [Y1,Y2,Co1,Cg1,Co2,Cg2] (codec/assemble.cl:27-37); warps share nothing, so there is no
+// CTA barrier at all.
+//   wavelet : per plane pair, levels 2..16 on both planes at once (lane = plane x row, then
+//             plane x column), then level 32 per plane (lane = row in registers, then lane =
+//             column); the (char)-truncated result goes to `res`.  The coefficients come
+//             straight from sym_t into registers as 16-byte pieces (rans_streams_kernel):
+//             row r of tile t' of a plane-group is run 4t' + r/8, pieces 2(r%8) and 2(r%8)+1.
+//   assembly: 4 DXT1 blocks (or 64 RGB8 texels) per lane and 4-row slab, coalesced 16-byte
+//             stores; palette index = run_end - S.  The index / palette loads of the next slab
+//             are in flight while a slab is assembled, those of slab 0 during the wavelet.
+constexpr int kWaWarps = 4;
+constexpr int kWaSmem = kWaWarps * kWarpWork;  // 36864
 
 template <int RGB>
-__global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const BatchParams p) {
+__global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(const BatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t smem_s = smem_u32(smem);
-  trap_unless_aligned(smem_s, kRing);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tabs_s = smem_s + kFusedTabOff;
-  const uint32_t x_s = smem_s + warp * kXBytes;
-  const uint32_t y_s = smem_s + kFusedYOff + warp * kYBytes;
-  const uint32_t stage0_s = smem_s + kFusedStageOff;
-  const uint32_t stage_s = stage0_s + warp * kStageBytes;  // this warp's plane
-  const uint32_t b = blockIdx.x / p.groups_per_plane;
-  const uint32_t g = blockIdx.x % p.groups_per_plane;
+  const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
+  const uint32_t wl_s = w_s + kWBytes;
+  const uint32_t res_s = wl_s + kWlowBytes;
+  const uint32_t tiles_per_image = p.n_blocks / kTileSyms;
+  const uint32_t gt_tile = blockIdx.x * kWaWarps + warp;  // tile index over the whole batch
+  const uint32_t b = gt_tile / tiles_per_image;
+  if (b >= p.n_images) return;
+  const uint32_t tile = gt_tile % tiles_per_image;
+  const uint32_t tiles_x = p.blocks_x / kTile;
+  const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
   const ImageStreams is = image_streams(p, b);
 
-  // Y table and chroma table of this image
-  load_table(tabs_s, p.tables + (4ull * b + 0) * kTableSize, threadIdx.x, kFusedWarps * 32);
-  load_table(tabs_s + kTableSize * 4, p.tables + (4ull * b + 1) * kTableSize, threadIdx.x, kFusedWarps * 32);
-  __syncthreads();
-
-  // ---- phase 1: rANS, warp = plane ------------------------------------------------------
-  // Y stream = Y1 || Y2, chroma stream = Co1 || Cg1 || Co2 || Cg2 (codec/encoder.cpp:87,93-95)
-  const bool chroma = warp >= 2;
-  const uint32_t group = (chroma ? warp - 2 : warp) * p.groups_per_plane + g;
-  {
-    const uint32_t run_s = stage_s + lane * 256;
-    const uint32_t sw = lane & 15;
-    rans_decode_group<true>(tabs_s + (chroma ? kTableSize * 4 : 0), is.payload + (chroma ? is.in_off[1] : is.in_off[0]),
-                            group, kLanes, x_s, p.cmp, p.cmp + p.cmp_bytes,
-                            [&](int m, uint32_t lo, uint32_t hi) { sts64(run_s + (((31 - m) ^ sw) << 3), lo, hi); });
-  }
-  __syncwarp();
-
-  if (p.tap_symbols) {
-    uint8_t *dst = p.tap_symbols + (chroma ? is.out_off[1] : is.out_off[0]) + static_cast<size_t>(group) * kGroupSyms;
-    for (uint32_t r = 0; r < kLanes; ++r) {
-      const uint2 v = lds64(stage_s + r * 256 + ((lane ^ (r & 15)) << 3));
-      *reinterpret_cast<uint2 *>(dst + r * 256 + lane * 8) = v;
-    }
-    __syncwarp();
-  }
-
-  // ---- phase 2: inverse wavelet of the 8 tiles of this plane -------------------------------
-  const uint32_t tiles_x = p.blocks_x / kTile;
-  const uint32_t tile0 = g * 8;
-  const uint32_t ty0 = tile0 / tiles_x, tx0 = tile0 % tiles_x;
-  const uint32_t wl = (lane & 16) ? y_s : x_s;  // this lane's Wlow area in the low levels
-
-#pragma unroll 1
-  for (uint32_t pair = 0; pair < 4; ++pair) {
-    // corners: lane -> (tile 2 pair + lane/16, row lane%16), bytes -> (byte - 128) as int16
-    {
-      const uint32_t t = 2 * pair + (lane >> 4), r = lane & 15;
-      // row r of tile t: run 4t + r/8, chunks 4 (r%8) + j; chunk position = chunk ^ (run & 15)
-      const uint32_t a0 = stage_s + (4 * t + (r >> 3)) * 256 + ((4 * ((r & 7) ^ (t & 3)) + (r >> 3)) << 3);
-      const uint2 a = lds64(a0), c = lds64(a0 ^ 8);
-      const uint32_t x0 = a.x ^ 0x80808080u, x1 = a.y ^ 0x80808080u, x2 = c.x ^ 0x80808080u, x3 = c.y ^ 0x80808080u;
-      const uint32_t row = wl + r * 32 + (((r >> 2) & 1) << 4);
-      sts128(row, sext_byte_pair<0>(x0), sext_byte_pair<2>(x0), sext_byte_pair<0>(x1), sext_byte_pair<2>(x1));
-      sts128(row ^ 16, sext_byte_pair<0>(x2), sext_byte_pair<2>(x2), sext_byte_pair<0>(x3), sext_byte_pair<2>(x3));
-    }
-    __syncwarp();
-    low_level<2>(wl, lane);
-    low_level<4>(wl, lane);
-    low_level<8>(wl, lane);
-    low_level<16>(wl, lane);
-
-#pragma unroll 1
-    for (uint32_t q = 0; q < 2; ++q) {
-      const uint32_t t = 2 * pair + q;
-      const uint32_t slot = stage_s + t * kTileSyms;  // this tile's 1 KiB of the stage
-      // ---- level 32, rows: lane = row
-      {
-        int v[32];
-        // symbol chunks j = 0..3 of row `lane` sit at sym0 ^ (8 j)
-        const uint32_t sym0 = slot + (lane >> 3) * 256 + ((4 * ((lane & 7) ^ (t & 3)) + (lane >> 3)) << 3);
-        if (lane < 16) {  // low half of rows 0..15 = the 16x16 result of the lower levels
-          const uint32_t row = (q ? y_s : x_s) + lane * 32 + (((lane >> 2) & 1) << 4);
-          const uint4 a = lds128(row), c = lds128(row ^ 16);
-          const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
-        } else {
-          const uint2 a = lds64(sym0), c = lds64(sym0 ^ 8);
-          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, c.x ^ 0x80808080u, c.y ^ 0x80808080u};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[4 * i] = sext_byte<0>(x[i]); v[4 * i + 1] = sext_byte<1>(x[i]);
-            v[4 * i + 2] = sext_byte<2>(x[i]); v[4 * i + 3] = sext_byte<3>(x[i]);
-          }
-        }
-        {
-          const uint2 a = lds64(sym0 ^ 16), c = lds64(sym0 ^ 24);
-          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, c.x ^ 0x80808080u, c.y ^ 0x80808080u};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[16 + 4 * i] = sext_byte<0>(x[i]); v[16 + 4 * i + 1] = sext_byte<1>(x[i]);
-            v[16 + 4 * i + 2] = sext_byte<2>(x[i]); v[16 + 4 * i + 3] = sext_byte<3>(x[i]);
-          }
-        }
-        __syncwarp();  // every lane holds its row: the tile's symbols and Wlow may be overwritten
-        inverse_lift<32>(v);
-        const uint32_t wrow = (lane < 16 ? x_s + lane * 64 : slot + (lane - 16) * 64) + (((lane >> 1) & 3) << 4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          sts128(wrow ^ (j << 4), pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
-                 pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
-      }
-      __syncwarp();
-      // ---- level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
-      // back into the tile's slot as row-major bytes
-      {
-        uint32_t colx[4], cols[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const uint32_t o = ((((lane >> 3) ^ s) & 3) << 4) + (lane & 7) * 2;
-          colx[s] = x_s + o;
-          cols[s] = slot + o - 16 * 64;
-        }
-        int v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lds_s16((i < 16 ? colx[(i >> 1) & 3] : cols[(i >> 1) & 3]) + i * 64);
-        __syncwarp();  // W is in registers: the slot may take the result
-        inverse_lift<32>(v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sts8(slot + i * 32 + lane, static_cast<uint32_t>(v[i]));
-        if (p.tap_planes) {
-          uint32_t tx = tx0 + t, ty = ty0;
-          while (tx >= tiles_x) { tx -= tiles_x; ++ty; }
-          int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + warp) * p.n_blocks +
-                       static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tp[static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i]);
-        }
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: assembly, codec/assemble.cl:64-129 -------------------------------------
+  // ---- assembly inputs of slab 0 start their trip now ---------------------------------
   const uint32_t n_entries = is.palette_bytes / 4;
   const bool pal_ok = static_cast<uint64_t>(is.pal_off) + is.palette_bytes <= p.palette_cap && n_entries > 0;
   const uint32_t *pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? is.pal_off : 0));
   const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
   const int32_t *run_end = p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane);
   const bool idx16 = p.idx16 != 0;
-  const uint32_t lane_row = lane >> 3, lane_col = 4 * (lane & 7);
-
-  // slab u = 8 * tile + k: rows 4k..4k+3 of tile (g * 8 + u / 8); first block of this lane
-  auto slab_gidx = [&](uint32_t u) -> uint32_t {
-    uint32_t tx = tx0 + (u >> 3), ty = ty0;
-    while (tx >= tiles_x) { tx -= tiles_x; ++ty; }
-    return (ty * kTile + 4 * (u & 7) + lane_row) * p.blocks_x + tx * kTile + lane_col;
-  };
-  // stage A: suffix sums + run end of the 4 blocks;  stage B: indices -> palette words
+  // first block of this lane in slab k (rows 4k..4k+3 of the tile)
+  const uint32_t gidx0 = (ty * kTile + (lane >> 3)) * p.blocks_x + tx * kTile + 4 * (lane & 7);
+  const uint32_t slab_stride = 4 * p.blocks_x;
   uint32_t sfx[4] = {0u, 0u, 0u, 0u}, re = 0u, word_nx[4] = {0u, 0u, 0u, 0u};
   auto load_sfx = [&](uint32_t gidx) {
+    // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
+    const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
     if (idx16) {
-      const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(p.idx_s) + img_block0 + gidx));
+      const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(p.idx_s) + e));
       sfx[0] = sv.x & 0xFFFFu; sfx[1] = sv.x >> 16; sfx[2] = sv.y & 0xFFFFu; sfx[3] = sv.y >> 16;
     } else {
-      const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + img_block0 + gidx));
+      const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + e));
       sfx[0] = sv.x; sfx[1] = sv.y; sfx[2] = sv.z; sfx[3] = sv.w;
     }
     re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
@@ -750,28 +643,117 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
     if (p.tap_indices)
       *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
   };
+  load_sfx(gidx0);
 
-  uint32_t gidx_b = slab_gidx(warp);  // gidx of the slab whose words are being loaded
-  load_sfx(gidx_b);
-  load_words(gidx_b);
-  if (warp + kFusedWarps < 64) {
-    gidx_b = slab_gidx(warp + kFusedWarps);
-    load_sfx(gidx_b);
-  }
+  // ---- stage 4: inverse wavelet ------------------------------------------------------------
+  // piece 0 of row (lane % 16 .. or lane) of this tile inside a plane-group; + 512 = piece 1
+  const uint32_t tq = tile & 7;
+  const uint8_t *sym_img = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(tile >> 3) * kGroupSyms;
+  const size_t plane_stride = static_cast<size_t>(p.groups_per_plane) * kGroupSyms;  // = N
+  const uint32_t row_piece = (2 * (lane & 7)) * 512 + (4 * tq + (lane >> 3)) * 16;          // row = lane
+  const uint32_t crn_piece = (2 * (lane & 7)) * 512 + (4 * tq + ((lane & 15) >> 3)) * 16;   // row = lane % 16
+  const uint32_t wl = wl_s + (lane >> 4) * 512;
 
 #pragma unroll 1
-  for (uint32_t u = warp; u < 64; u += kFusedWarps) {
-    const uint32_t gidx = slab_gidx(u);
-    uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
-    if (u + kFusedWarps < 64) load_words(gidx_b);  // sfx / re of slab u + 6 arrived during slab u - 6
-    if (u + 2 * kFusedWarps < 64) {
-      gidx_b = slab_gidx(u + 2 * kFusedWarps);
-      load_sfx(gidx_b);
+  for (uint32_t pair = 0; pair < 3; ++pair) {
+    const uint8_t *plane_a = sym_img + (2 * pair) * plane_stride;
+    // corners: lane -> (plane 2 pair + lane/16, row lane%16), bytes -> (byte - 128) as int16
+    {
+      const uint4 c = __ldg(reinterpret_cast<const uint4 *>(plane_a + (lane >> 4) * plane_stride + crn_piece));
+      const uint32_t x0 = c.x ^ 0x80808080u, x1 = c.y ^ 0x80808080u, x2 = c.z ^ 0x80808080u, x3 = c.w ^ 0x80808080u;
+      const uint32_t r = lane & 15;
+      const uint32_t row = wl + r * 32 + (((r >> 2) & 1) << 4);
+      sts128(row, sext_byte_pair<0>(x0), sext_byte_pair<2>(x0), sext_byte_pair<0>(x1), sext_byte_pair<2>(x1));
+      sts128(row ^ 16, sext_byte_pair<0>(x2), sext_byte_pair<2>(x2), sext_byte_pair<0>(x3), sext_byte_pair<2>(x3));
     }
-    const uint32_t src = stage0_s + u * 128 + lane * 4;  // rows 4k..4k+3 of the tile, 4 bytes per lane
+    // the level-32 rows of both planes (high half of rows 0..15, whole rows 16..31)
+    uint4 pc[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      pc[q][1] = __ldg(reinterpret_cast<const uint4 *>(plane_a + q * plane_stride + row_piece + 512));
+      pc[q][0] = lane < 16 ? make_uint4(0u, 0u, 0u, 0u)
+                           : __ldg(reinterpret_cast<const uint4 *>(plane_a + q * plane_stride + row_piece));
+    }
+    __syncwarp();
+    low_level<2>(wl, lane);
+    low_level<4>(wl, lane);
+    low_level<8>(wl, lane);
+    low_level<16>(wl, lane);
+
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t pl = 2 * pair + q;
+      // ---- level 32, rows: lane = row
+      {
+        int v[32];
+        if (lane < 16) {  // low half of rows 0..15 = the 16x16 result of the lower levels
+          const uint32_t row = wl_s + q * 512 + lane * 32 + (((lane >> 2) & 1) << 4);
+          const uint4 a = lds128(row), c = lds128(row ^ 16);
+          const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
+        } else {
+          const uint32_t x[4] = {pc[q][0].x ^ 0x80808080u, pc[q][0].y ^ 0x80808080u, pc[q][0].z ^ 0x80808080u, pc[q][0].w ^ 0x80808080u};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[4 * i] = sext_byte<0>(x[i]); v[4 * i + 1] = sext_byte<1>(x[i]);
+            v[4 * i + 2] = sext_byte<2>(x[i]); v[4 * i + 3] = sext_byte<3>(x[i]);
+          }
+        }
+        {
+          const uint32_t x[4] = {pc[q][1].x ^ 0x80808080u, pc[q][1].y ^ 0x80808080u, pc[q][1].z ^ 0x80808080u, pc[q][1].w ^ 0x80808080u};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[16 + 4 * i] = sext_byte<0>(x[i]); v[16 + 4 * i + 1] = sext_byte<1>(x[i]);
+            v[16 + 4 * i + 2] = sext_byte<2>(x[i]); v[16 + 4 * i + 3] = sext_byte<3>(x[i]);
+          }
+        }
+        inverse_lift<32>(v);
+        const uint32_t wrow = w_s + lane * 64 + (((lane >> 1) & 3) << 4);  // logical chunk 0
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(wrow ^ (j << 4), pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
+                 pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
+      }
+      __syncwarp();
+      // ---- level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
+      {
+        uint32_t col[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) col[s] = w_s + ((((lane >> 3) ^ s) & 3) << 4) + (lane & 7) * 2;
+        int v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = lds_s16(col[(i >> 1) & 3] + i * 64);
+        inverse_lift<32>(v);
+        const uint32_t rs = res_s + pl * kTileSyms + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sts8(rs + i * 32, static_cast<uint32_t>(v[i]));
+        if (p.tap_planes) {
+          int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + pl) * p.n_blocks +
+                       static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tp[static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i]);
+        }
+      }
+      __syncwarp();
+    }
+    if (pair == 0) {  // slab 0: indices -> palette words; slab 1: suffix sums
+      load_words(gidx0);
+      load_sfx(gidx0 + slab_stride);
+    }
+  }
+
+  // ---- stage 5: assembly, codec/assemble.cl:64-129 ---------------------------------------
+#pragma unroll 1
+  for (uint32_t k = 0; k < 8; ++k) {
+    const uint32_t gidx = gidx0 + k * slab_stride;
+    const uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
+    if (k + 1 < 8) load_words(gidx + slab_stride);  // its sfx / re arrived during slab k - 1
+    if (k + 2 < 8) load_sfx(gidx + 2 * slab_stride);
+    const uint32_t src = res_s + k * 128 + lane * 4;  // rows 4k..4k+3 of the tile, 4 bytes per lane
     uint32_t pw[6];
 #pragma unroll
-    for (int pl = 0; pl < 6; ++pl) pw[pl] = lds32(src + pl * kStageBytes);
+    for (int pl = 0; pl < 6; ++pl) pw[pl] = lds32(src + pl * kTileSyms);
 
     int y1[4], y2[4], co1[4], cg1[4], co2[4], cg2[4];
     sext4(pw[0], y1); sext4(pw[1], y2); sext4(pw[2], co1); sext4(pw[3], cg1); sext4(pw[4], co2); sext4(pw[5], cg2);
@@ -813,11 +795,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) fused_planes_kernel(const
 #pragma unroll
         for (int s = 0; s < 4; ++s) pal4[j][s] = e[s];
       }
-      // texel coordinates of this lane's first block
       const size_t img_w = 4ull * p.blocks_x;
       uint8_t *img = p.out + static_cast<size_t>(b) * p.n_blocks * 48;
-      const uint32_t by = gidx / p.blocks_x, bx = gidx - by * p.blocks_x;
-      const size_t x0 = 4ull * bx, y0 = 4ull * by;
+      const size_t x0 = 4ull * (tx * kTile + 4 * (lane & 7)), y0 = 4ull * (ty * kTile + 4 * k + (lane >> 3));
 #pragma unroll
       for (int yy = 0; yy < 4; ++yy) {
         uint32_t t[16];  // 16 texels of this texel row, r | g << 8 | b << 16
@@ -867,11 +847,11 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
   __syncthreads();
   const uint32_t group = blockIdx.x * kPlainWarps + warp;
   if (group >= n_groups) return;
-  uint8_t *dst = out + (static_cast<size_t>(group) * n_lanes + lane) * kSymsPerLane + 248;
+  uint8_t *dst = out + (static_cast<size_t>(group) * n_lanes + lane) * kSymsPerLane + 240;
   const bool active = lane < n_lanes;
   rans_decode_group<false>(tab_s, data, group, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
-                           [&](int m, uint32_t lo, uint32_t hi) {
-                             if (active) *reinterpret_cast<uint2 *>(dst - 8 * m) = make_uint2(lo, hi);
+                           [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                             if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w0, w1, w2, w3);
                            });
 }
 
@@ -888,11 +868,11 @@ cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_
 
 static cudaError_t ensure_attrs() {
   static cudaError_t once = []() {
-    cudaError_t e = cudaFuncSetAttribute(fused_planes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem);
+    cudaError_t e = cudaFuncSetAttribute(wavelet_assemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fused_planes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem);
+    e = cudaFuncSetAttribute(wavelet_assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(side_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSideSmem);
+    e = cudaFuncSetAttribute(rans_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRansSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ans_decode_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem);
   }();
@@ -911,11 +891,13 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s);
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
-  // palette + index streams
-  const uint32_t max_pal_groups = max_palette_bytes / kGroupSyms;
-  const uint32_t pal_ctas = (max_pal_groups + kSideWarps - 1) / kSideWarps;
-  const uint32_t idx_ctas = (p.groups_per_plane + kSideWarps - 1) / kSideWarps;
-  side_streams_kernel<<<p.n_images * (pal_ctas + idx_ctas), kSideWarps * 32, kSideSmem, s>>>(p, pal_ctas, idx_ctas);
+  // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
+  StreamGrid sg;
+  sg.y_ctas = (2 * p.groups_per_plane + kRansWarps - 1) / kRansWarps;
+  sg.c_ctas = (4 * p.groups_per_plane + kRansWarps - 1) / kRansWarps;
+  sg.pal_ctas = (max_palette_bytes / kGroupSyms + kRansWarps - 1) / kRansWarps;
+  sg.idx_ctas = (p.groups_per_plane + kRansWarps - 1) / kRansWarps;
+  rans_streams_kernel<<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
@@ -923,11 +905,13 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
-  const uint32_t grid = p.n_images * p.groups_per_plane;
+  // stages 4 + 5: one warp per tile
+  const uint64_t tiles = static_cast<uint64_t>(p.n_images) * (p.n_blocks / kTileSyms);
+  const uint32_t grid = static_cast<uint32_t>((tiles + kWaWarps - 1) / kWaWarps);
   if (rgb_mode)
-    fused_planes_kernel<1><<<grid, kFusedWarps * 32, kFusedSmem, s>>>(p);
+    wavelet_assemble_kernel<1><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
   else
-    fused_planes_kernel<0><<<grid, kFusedWarps * 32, kFusedSmem, s>>>(p);
+    wavelet_assemble_kernel<0><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return stamp();

@@ -4,9 +4,9 @@
 // Reference stages (citations relative to the reference tree):
 //   1. ans/build_table.cl:12-83           -> build_tables_kernel
 //   2. ans/ans_decode.cl:25-143           -> rans_decode_group() inside every decode kernel
-//   3. codec/decode_indices.cl:6-84       -> index_stream_kernel (scan fused behind the rANS warp)
-//   4. codec/inverse_wavelet.cl:69-192    -> fused_planes_kernel, phase 2
-//   5. codec/assemble.cl:64-129           -> fused_planes_kernel, phase 3
+//   3. codec/decode_indices.cl:6-84       -> rans_streams_kernel (scan fused behind the rANS warp) + index_carry_kernel
+//   4. codec/inverse_wavelet.cl:69-192    -> wavelet_assemble_kernel
+//   5. codec/assemble.cl:64-129           -> wavelet_assemble_kernel
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,9 +43,10 @@ struct BatchParams {
   uint32_t groups_per_plane; // N / 8192
   // scratch
   uint32_t *tables;          // [B][4][2048] packed entries
+  uint8_t *sym_t;            // [B][6 * N/8192 plane-groups][16][32][16 B]: plane symbols, transposed (gst_kernels.cu)
   uint8_t *palette;          // compact: image b at pal_off(b) = out_off[4b+2] - 7N*b - 6N
   uint64_t palette_cap;      // bytes available in `palette`
-  void *idx_s;               // [B][N] u16 or u32: sum of the index deltas after block i in its 256-block run
+  void *idx_s;               // [B][N] u16 or u32, transposed like sym_t: sum of the index deltas after block i in its 256-block run
   uint32_t idx16;            // 1: idx_s holds u16 (every palette <= 65536 entries), 0: u32
   int32_t *run_end;          // [B][N/256] inclusive index prefix at the end of every run
   int32_t *idx_total;        // [B][N/8192] sum of every index group

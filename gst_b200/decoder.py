@@ -266,7 +266,7 @@ class Decoder:
             self.sync(s)
 
     # -- profiling -----------------------------------------------------------------------
-    KERNEL_NAMES = ("build_tables", "side_streams", "index_carry", "fused_planes")
+    KERNEL_NAMES = ("build_tables", "rans_streams", "index_carry", "wavelet_assemble")
 
     def profile(self, on=True):
         check(lib().gst_profile_enable(self.ctx, 1 if on else 0))
