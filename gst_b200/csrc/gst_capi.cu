@@ -752,9 +752,11 @@ int gst_ans_table(gst_ans_decoder *d, uint8_t *symbols, uint16_t *freqs, uint16_
   GST_CUDA_TRY(cudaMemcpy(t.data(), d->table, t.size() * 4, cudaMemcpyDeviceToHost));
   for (uint32_t slot = 0; slot < gst::kTableSize; ++slot) {
     const uint32_t e = t[slot];
-    if (symbols) symbols[slot] = static_cast<uint8_t>(e & 0xFF);
-    if (freqs) freqs[slot] = static_cast<uint16_t>((e >> 8) & 0xFFF);
-    if (cum_freqs) cum_freqs[slot] = static_cast<uint16_t>(slot - (e >> 20));
+    uint32_t sym, freq, cum;
+    gst::unpack_entry(e, slot, &sym, &freq, &cum);
+    if (symbols) symbols[slot] = static_cast<uint8_t>(sym);
+    if (freqs) freqs[slot] = static_cast<uint16_t>(freq);
+    if (cum_freqs) cum_freqs[slot] = static_cast<uint16_t>(cum);
   }
   return GST_OK;
 }

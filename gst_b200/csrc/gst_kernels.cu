@@ -123,7 +123,7 @@ __device__ __forceinline__ uint32_t pack16(int a, int b) {
 // always complete.
 //
 // Per symbol and lane (ans/ans_decode.cl:38-65):
-//   e = table[state & 2047];  state = (state >> 11) * e.freq + e.bias          (bias = slot - cum)
+//   e = table[state & 2047];  state = (state >> 11) * e.freq + slot - e.cum   (as umulhi, see gst_kernels.cuh)
 //   lanes whose state fell below L = 2^15 take the next 16-bit word, higher lanes first:
 //   word index = next - 1 - popc(ballot & lanes_above_me);  next -= popc(ballot)
 // The word load is unconditional (every lane's address lies inside the staged 64 bytes), only
@@ -192,17 +192,27 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        uint32_t slot_a;  // tab_s + 4 * (state & 2047): one LOP3 + one IMAD
+        uint32_t slot_a;  // tab_s + 4 * (state & 2047)
         asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(state & (kTableSize - 1)), "r"(tab_s));
         const uint32_t e = lds32(slot_a);
-        state = (state >> kTableLog) * ((e >> 8) & 0xFFFu) + (e >> 20);
+        // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  Written as multiplies so
+        // that the shifts issue on the FMA pipe: the ALU pipe (LOP3 / PRMT / ISETP) is the busy one.
+        uint32_t f21, sym24, hi;
+        int32_t bias;
+        asm("mul.lo.u32 %0, %1, 2097152;" : "=r"(f21) : "r"(e));   // e << 21
+        asm("mul.hi.s32 %0, %1, 8192;" : "=r"(bias) : "r"(e));     // (int)e >> 19
+        asm("mul.lo.u32 %0, %1, 8192;" : "=r"(sym24) : "r"(e));    // e << 13: symbol in the top byte
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(state), "r"(f21));
+        state = hi + static_cast<uint32_t>(bias);
         const bool need = FULL ? (state < kRansL) : (active && state < kRansL);
         const uint32_t mask = __ballot_sync(0xffffffffu, need);
         const uint32_t a = cur2 - 2u * __popc(mask & gt);
         const uint32_t w = lds_u16(ring_s | (a & (kRing - 1)));
-        if (need) state = __byte_perm(w, state, 0x5410);  // state << 16 | w
-        cur2 -= 2u * __popc(mask);                        // ans/ans_decode.cl:65
-        acc[3 - h] = __byte_perm(acc[3 - h], e, 0x2104);  // acc << 8 | symbol
+        uint32_t renorm;  // state << 16 | w
+        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state), "r"(w));
+        if (need) state = renorm;
+        cur2 -= 2u * __popc(mask);                              // ans/ans_decode.cl:65
+        acc[3 - h] = __byte_perm(acc[3 - h], sym24, 0x2107);    // acc << 8 | symbol
       }
     }
     emit(m, acc[0], acc[1], acc[2], acc[3]);
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__rest
   for (int i = 0; i < 8; ++i) {
     const uint32_t slot = t * 8 + i;
     const uint32_t sym = max(v[i], prev);
-    out[slot] = pack_entry(sym, s_freq[sym], (slot - s_cum[sym]) & 0xFFFu);
+    out[slot] = pack_entry(sym, s_freq[sym], slot, s_cum[sym]);
   }
 }
 
@@ -619,60 +629,77 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
   // first block of this lane in slab k (rows 4k..4k+3 of the tile)
   const uint32_t gidx0 = (ty * kTile + (lane >> 3)) * p.blocks_x + tx * kTile + 4 * (lane & 7);
   const uint32_t slab_stride = 4 * p.blocks_x;
-  uint32_t sfx[4] = {0u, 0u, 0u, 0u}, re = 0u, word_nx[4] = {0u, 0u, 0u, 0u};
-  auto load_sfx = [&](uint32_t gidx) {
+  // S of 4 blocks (raw) + the run end; words = the 4 palette words
+  struct Sfx { uint4 raw; uint32_t re; };
+  auto load_sfx = [&](uint32_t gidx) -> Sfx {
     // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
     const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
+    Sfx r;
     if (idx16) {
       const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(p.idx_s) + e));
-      sfx[0] = sv.x & 0xFFFFu; sfx[1] = sv.x >> 16; sfx[2] = sv.y & 0xFFFFu; sfx[3] = sv.y >> 16;
+      r.raw = make_uint4(sv.x, sv.y, 0u, 0u);
     } else {
-      const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + e));
-      sfx[0] = sv.x; sfx[1] = sv.y; sfx[2] = sv.z; sfx[3] = sv.w;
+      r.raw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + e));
     }
-    re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
+    r.re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
+    return r;
   };
-  auto load_words = [&](uint32_t gidx) {
+  uint32_t word_nx[4] = {0u, 0u, 0u, 0u};
+  auto load_words = [&](const Sfx &sf, uint32_t gidx) {
+    uint32_t sfx[4];
+    if (idx16) {
+      sfx[0] = sf.raw.x & 0xFFFFu; sfx[1] = sf.raw.x >> 16; sfx[2] = sf.raw.y & 0xFFFFu; sfx[3] = sf.raw.y >> 16;
+    } else {
+      sfx[0] = sf.raw.x; sfx[1] = sf.raw.y; sfx[2] = sf.raw.z; sfx[3] = sf.raw.w;
+    }
     uint32_t idx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      idx[j] = re - sfx[j];
+      idx[j] = sf.re - sfx[j];
       if (idx16) idx[j] &= 0xFFFFu;
       word_nx[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
     }
     if (p.tap_indices)
       *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
   };
-  load_sfx(gidx0);
+
+  // ---- the tile's coefficients: sym_t -> res, one cp.async group per plane pair ------------------
+  // 16-byte piece (row r, half j) of tile tq of a plane-group sits at [k = 2 (r % 8) + j][run 4 tq + r / 8]
+  // (rans_streams_kernel); res[plane] receives the tile row-major, and later its int8 result.
+  {
+    const uint32_t tq = tile & 7;
+    const uint8_t *src0 = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(tile >> 3) * kGroupSyms;
+    const size_t plane_stride = static_cast<size_t>(p.groups_per_plane) * kGroupSyms;  // = N
+#pragma unroll
+    for (int pl = 0; pl < 6; ++pl) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t pc = lane + 32 * i, r = pc >> 1, j = pc & 1;
+        cp_async16(res_s + pl * kTileSyms + pc * 16,
+                   src0 + pl * plane_stride + (2 * (r & 7) + j) * 512 + (4 * tq + (r >> 3)) * 16);
+      }
+      if (pl & 1) cp_async_commit();
+    }
+  }
+  Sfx sa = load_sfx(gidx0), sb = load_sfx(gidx0 + slab_stride);
 
   // ---- stage 4: inverse wavelet ------------------------------------------------------------
-  // piece 0 of row (lane % 16 .. or lane) of this tile inside a plane-group; + 512 = piece 1
-  const uint32_t tq = tile & 7;
-  const uint8_t *sym_img = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(tile >> 3) * kGroupSyms;
-  const size_t plane_stride = static_cast<size_t>(p.groups_per_plane) * kGroupSyms;  // = N
-  const uint32_t row_piece = (2 * (lane & 7)) * 512 + (4 * tq + (lane >> 3)) * 16;          // row = lane
-  const uint32_t crn_piece = (2 * (lane & 7)) * 512 + (4 * tq + ((lane & 15) >> 3)) * 16;   // row = lane % 16
   const uint32_t wl = wl_s + (lane >> 4) * 512;
 
 #pragma unroll 1
   for (uint32_t pair = 0; pair < 3; ++pair) {
-    const uint8_t *plane_a = sym_img + (2 * pair) * plane_stride;
+    if (pair == 0) cp_async_wait_group<2>();
+    else if (pair == 1) cp_async_wait_group<1>();
+    else cp_async_wait_group<0>();
+    __syncwarp();
     // corners: lane -> (plane 2 pair + lane/16, row lane%16), bytes -> (byte - 128) as int16
     {
-      const uint4 c = __ldg(reinterpret_cast<const uint4 *>(plane_a + (lane >> 4) * plane_stride + crn_piece));
-      const uint32_t x0 = c.x ^ 0x80808080u, x1 = c.y ^ 0x80808080u, x2 = c.z ^ 0x80808080u, x3 = c.w ^ 0x80808080u;
       const uint32_t r = lane & 15;
+      const uint4 c = lds128(res_s + (2 * pair + (lane >> 4)) * kTileSyms + r * 32);
+      const uint32_t x0 = c.x ^ 0x80808080u, x1 = c.y ^ 0x80808080u, x2 = c.z ^ 0x80808080u, x3 = c.w ^ 0x80808080u;
       const uint32_t row = wl + r * 32 + (((r >> 2) & 1) << 4);
       sts128(row, sext_byte_pair<0>(x0), sext_byte_pair<2>(x0), sext_byte_pair<0>(x1), sext_byte_pair<2>(x1));
       sts128(row ^ 16, sext_byte_pair<0>(x2), sext_byte_pair<2>(x2), sext_byte_pair<0>(x3), sext_byte_pair<2>(x3));
-    }
-    // the level-32 rows of both planes (high half of rows 0..15, whole rows 16..31)
-    uint4 pc[2][2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      pc[q][1] = __ldg(reinterpret_cast<const uint4 *>(plane_a + q * plane_stride + row_piece + 512));
-      pc[q][0] = lane < 16 ? make_uint4(0u, 0u, 0u, 0u)
-                           : __ldg(reinterpret_cast<const uint4 *>(plane_a + q * plane_stride + row_piece));
     }
     __syncwarp();
     low_level<2>(wl, lane);
@@ -680,9 +707,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
     low_level<8>(wl, lane);
     low_level<16>(wl, lane);
 
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
+#pragma unroll 1
+    for (uint32_t q = 0; q < 2; ++q) {
       const uint32_t pl = 2 * pair + q;
+      const uint32_t rs = res_s + pl * kTileSyms;
       // ---- level 32, rows: lane = row
       {
         int v[32];
@@ -693,7 +721,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
 #pragma unroll
           for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
         } else {
-          const uint32_t x[4] = {pc[q][0].x ^ 0x80808080u, pc[q][0].y ^ 0x80808080u, pc[q][0].z ^ 0x80808080u, pc[q][0].w ^ 0x80808080u};
+          const uint4 a = lds128(rs + lane * 32);
+          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, a.z ^ 0x80808080u, a.w ^ 0x80808080u};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             v[4 * i] = sext_byte<0>(x[i]); v[4 * i + 1] = sext_byte<1>(x[i]);
@@ -701,7 +730,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
           }
         }
         {
-          const uint32_t x[4] = {pc[q][1].x ^ 0x80808080u, pc[q][1].y ^ 0x80808080u, pc[q][1].z ^ 0x80808080u, pc[q][1].w ^ 0x80808080u};
+          const uint4 a = lds128(rs + lane * 32 + 16);
+          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, a.z ^ 0x80808080u, a.w ^ 0x80808080u};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             v[16 + 4 * i] = sext_byte<0>(x[i]); v[16 + 4 * i + 1] = sext_byte<1>(x[i]);
@@ -715,7 +745,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
           sts128(wrow ^ (j << 4), pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
                  pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
       }
-      __syncwarp();
+      __syncwarp();  // W complete, and every lane is done with the plane's coefficients in res
       // ---- level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
       {
         uint32_t col[4];
@@ -725,9 +755,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = lds_s16(col[(i >> 1) & 3] + i * 64);
         inverse_lift<32>(v);
-        const uint32_t rs = res_s + pl * kTileSyms + lane;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sts8(rs + i * 32, static_cast<uint32_t>(v[i]));
+        for (int i = 0; i < 32; ++i) sts8(rs + lane + i * 32, static_cast<uint32_t>(v[i]));
         if (p.tap_planes) {
           int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + pl) * p.n_blocks +
                        static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
@@ -737,9 +766,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
       }
       __syncwarp();
     }
-    if (pair == 0) {  // slab 0: indices -> palette words; slab 1: suffix sums
-      load_words(gidx0);
-      load_sfx(gidx0 + slab_stride);
+    if (pair == 0) {  // slab 0: indices -> palette words;  slabs 1, 2: suffix sums in flight
+      load_words(sa, gidx0);
+      sa = sb;
+      sb = load_sfx(gidx0 + 2 * slab_stride);
     }
   }
 
@@ -748,8 +778,9 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
   for (uint32_t k = 0; k < 8; ++k) {
     const uint32_t gidx = gidx0 + k * slab_stride;
     const uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
-    if (k + 1 < 8) load_words(gidx + slab_stride);  // its sfx / re arrived during slab k - 1
-    if (k + 2 < 8) load_sfx(gidx + 2 * slab_stride);
+    if (k + 1 < 8) load_words(sa, gidx + slab_stride);  // its S / run end were requested two slabs ago
+    sa = sb;
+    if (k + 3 < 8) sb = load_sfx(gidx + 3 * slab_stride);
     const uint32_t src = res_s + k * 128 + lane * 4;  // rows 4k..4k+3 of the tile, 4 bytes per lane
     uint32_t pw[6];
 #pragma unroll

@@ -22,11 +22,29 @@ constexpr uint32_t kRansL = 16u << kTableLog; // ans/ans_decode.cl:7-8  k*M = 2^
 constexpr int kTile = 32;                     // codec/codec_base.h:22 kWaveletBlockDim
 constexpr int kTileSyms = kTile * kTile;
 
-// Packed decode-table entry (internal scratch format, 4 B instead of the reference's
-// 6 B AnsTableEntry, codec/decoder.cpp:20-24):  sym | freq << 8 | (slot - cum_freq) << 20,
-// so that  state' = (state >> 11) * freq + bias  needs no separate cum_freq / slot add.
-__host__ __device__ inline uint32_t pack_entry(uint32_t sym, uint32_t freq, uint32_t bias) {
-  return (sym & 0xFFu) | ((freq & 0xFFFu) << 8) | (bias << 20);
+// Packed decode-table entry (internal scratch format, 4 B instead of the reference's 6 B
+// AnsTableEntry, codec/decoder.cpp:20-24):
+//     bits 0..10   freq           (2048, the single-symbol table, is stored as 0)
+//     bits 11..18  symbol
+//     bits 19..31  bias' = (slot - cum_freq) - ((slot * freq) >> 11), signed
+// With F = freq << 21 (= entry << 21) the reference update
+//     state' = (state >> 11) * freq + slot - cum_freq          (ans/ans_decode.cl:38-41)
+// equals  umulhi(state, F) + bias'  exactly, because  state * freq = (state >> 11) * freq * 2048
+// + slot * freq  and  slot = state & 2047:  the decode loop needs one shift-free multiply-high
+// on the FMA pipe instead of three shifts and a mask on the ALU pipe.  A single-symbol table
+// (freq = 2048) decodes to that symbol whatever the state does, so F = 0 is harmless there.
+__host__ __device__ inline uint32_t pack_entry(uint32_t sym, uint32_t freq, uint32_t slot, uint32_t cum) {
+  const uint32_t f = freq & 0x7FFu;
+  const int32_t bias = static_cast<int32_t>(slot - cum) - static_cast<int32_t>((slot * f) >> 11);
+  return f | ((sym & 0xFFu) << 11) | (static_cast<uint32_t>(bias) << 19);
+}
+// {symbol, freq, cum_freq} of slot `slot` back from a packed entry (table read-back API)
+__host__ __device__ inline void unpack_entry(uint32_t e, uint32_t slot, uint32_t *sym, uint32_t *freq, uint32_t *cum) {
+  const uint32_t f = e & 0x7FFu;
+  *sym = (e >> 11) & 0xFFu;
+  *freq = f ? f : 2048u;
+  const int32_t bias = (static_cast<int32_t>(e) >> 19) + static_cast<int32_t>((slot * f) >> 11);
+  *cum = slot - static_cast<uint32_t>(bias);
 }
 
 // Geometry + buffer description of one LoadCompressedDXTs-style call.  The compressed
