@@ -113,14 +113,14 @@ __device__ __forceinline__ uint32_t pack16(int a, int b) {
 // a group ends with its n_lanes 32-bit states, preceded by the shared 16-bit renorm words,
 // which are consumed backwards, higher lanes first (ans/ans_decode.cl:30-32,51-65).
 //
-// The renorm words are staged through a per-warp, 1 KiB-aligned shared-memory ring filled with
-// cp.async in 256-byte, 256-byte-aligned chunks (group ranges are only 4-byte aligned, so the
-// windows are aligned down in absolute address space and the ring is indexed by the low
-// address bits).  A checkpoint every 4 symbols (which consume at most 4*32*2 = 256 B) tops the
-// ring up whenever fewer than 768 B are staged and then waits until at most the two newest
-// cp.async groups are pending: a chunk has two checkpoint intervals to land, and because at
-// least 512 B are staged at every checkpoint, the 256 B the next four symbols can touch are
-// always complete.
+// The renorm words are staged through a per-warp, 2 KiB-aligned shared-memory ring filled with
+// cp.async in 512-byte, 512-byte-aligned chunks (one 16-byte copy per lane; group ranges are
+// only 4-byte aligned, so the windows are aligned down in absolute address space and the ring
+// is indexed by the low address bits).  A checkpoint every 8 symbols (which consume at most
+// 8*32*2 = 512 B) tops the ring up whenever fewer than 1536 B are staged and then waits until at
+// most the two newest cp.async groups are pending: a chunk has two checkpoint intervals to
+// land, and because at least 1024 B are staged at every checkpoint, the 512 B the next eight
+// symbols can touch are always complete.
 //
 // Per symbol and lane (ans/ans_decode.cl:38-65):
 //   e = table[state & 2047];  state = (state >> 11) * e.freq + slot - e.cum   (as umulhi, see gst_kernels.cuh)
@@ -128,8 +128,8 @@ __device__ __forceinline__ uint32_t pack16(int a, int b) {
 //   word index = next - 1 - popc(ballot & lanes_above_me);  next -= popc(ballot)
 // The word load is unconditional (every lane's address lies inside the staged 64 bytes), only
 // the state update is predicated.
-constexpr int kRing = 1024;
-constexpr int kChunk = 256;
+constexpr int kRing = 2048;
+constexpr int kChunk = 512;
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -159,14 +159,14 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
   // ans/ans_decode.cl:31
   uint32_t state = active ? __ldg(reinterpret_cast<const uint32_t *>(a_pos) + lane) : 0u;
 
-  // preload [c_top - 1024, c_top), c_top = a_pos rounded up to 256
+  // preload [c_top - 2048, c_top), c_top = a_pos rounded up to 512
   const uintptr_t lo16 = (reinterpret_cast<uintptr_t>(buf_lo) + 15) & ~static_cast<uintptr_t>(15);
   const uintptr_t hi16 = reinterpret_cast<uintptr_t>(buf_hi) & ~static_cast<uintptr_t>(15);
-  const uintptr_t c_top = (a_pos + 255) & ~static_cast<uintptr_t>(255);
-  uintptr_t lo = c_top - 4 * kChunk;
+  const uintptr_t c_top = (a_pos + (kChunk - 1)) & ~static_cast<uintptr_t>(kChunk - 1);
+  uintptr_t lo = c_top - kRing;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const uintptr_t a = lo + 16 * lane + 512 * i;
+  for (int i = 0; i < kRing / kChunk; ++i) {
+    const uintptr_t a = lo + 16 * lane + kChunk * i;
     if (a >= lo16 && a + 16 <= hi16) cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
   }
   cp_async_commit();
@@ -179,19 +179,18 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
   for (int m = 0; m < 16; ++m) {
     uint32_t acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      // checkpoint: top up when < 768 B are staged, then let the two newest groups fly
-      if (cur2 + 2u - static_cast<uint32_t>(lo) < 768u) {
+    for (int h = 0; h < 2; ++h) {
+      // checkpoint: top up when < 1536 B are staged, then let the two newest groups fly
+      if (cur2 + 2u - static_cast<uint32_t>(lo) < static_cast<uint32_t>(kRing - kChunk)) {
         lo -= kChunk;
         const uintptr_t a = lo + 16 * lane;
-        if (lane < 16 && a >= lo16 && a + 16 <= hi16)
-          cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+        if (a >= lo16 && a + 16 <= hi16) cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
       }
       cp_async_commit();
       cp_async_wait_group<2>();
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         uint32_t slot_a;  // tab_s + 4 * (state & 2047)
         asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(state & (kTableSize - 1)), "r"(tab_s));
         const uint32_t e = lds32(slot_a);
@@ -207,12 +206,15 @@ __device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t 
         const bool need = FULL ? (state < kRansL) : (active && state < kRansL);
         const uint32_t mask = __ballot_sync(0xffffffffu, need);
         const uint32_t a = cur2 - 2u * __popc(mask & gt);
-        const uint32_t w = lds_u16(ring_s | (a & (kRing - 1)));
+        uint32_t ra;  // ring_s | (a & (kRing - 1)) in one LOP3 (the ring is kRing-aligned)
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(a), "n"(kRing - 1), "r"(ring_s));  // (a & mask) | ring
+        const uint32_t w = lds_u16(ra);
         uint32_t renorm;  // state << 16 | w
         asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state), "r"(w));
         if (need) state = renorm;
         cur2 -= 2u * __popc(mask);                              // ans/ans_decode.cl:65
-        acc[3 - h] = __byte_perm(acc[3 - h], sym24, 0x2107);    // acc << 8 | symbol
+        const int word = 3 - 2 * h - (k >> 2);
+        acc[word] = __byte_perm(acc[word], sym24, 0x2107);      // acc << 8 | symbol
       }
     }
     emit(m, acc[0], acc[1], acc[2], acc[3]);
@@ -344,7 +346,7 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 //       difference exact), else as 32 bits, in the same transposed order as sym_t:
 //       [group][k][lane][16 values].
 constexpr int kRansWarps = 8;
-constexpr int kRansSmem = kRansWarps * kRing + kTableSize * 4;
+constexpr int kRansSmem = kRansWarps * kRing + kTableSize * 4 + kRing;  // + alignment slack
 
 // CTAs of one image: [Y][chroma][palette][index]
 struct StreamGrid {
@@ -354,8 +356,9 @@ struct StreamGrid {
 
 __global__ void __launch_bounds__(kRansWarps * 32, 8) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t smem_s = smem_u32(smem);
-  trap_unless_aligned(smem_s, kRing);
+  // the rings are indexed by OR-ing low address bits, so they must be kRing-aligned; the dynamic
+  // shared window itself is only guaranteed 1 KiB alignment, hence kRing bytes of slack
+  const uint32_t smem_s = (smem_u32(smem) + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring_s = smem_s + warp * kRing;
   const uint32_t tab_s = smem_s + kRansWarps * kRing;
@@ -605,7 +608,7 @@ constexpr int kWaSmem = kWaWarps * kWarpWork;  // 36864
 
 template <int RGB>
 __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(const BatchParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(2048) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
   const uint32_t wl_s = w_s + kWBytes;
@@ -863,15 +866,14 @@ __global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(cons
 // single table: the `ans_decode` kernel of ans/ans_decode.cl:76-95 as driven by
 // ans/ans_ocl.cpp:159-345.  Output: group * n_lanes * 256 + lane * 256 + position.
 constexpr int kPlainWarps = 8;
-constexpr int kPlainSmem = kPlainWarps * kRing + kTableSize * 4;
+constexpr int kPlainSmem = kPlainWarps * kRing + kTableSize * 4 + kRing;  // + alignment slack
 
 __global__ void __launch_bounds__(kPlainWarps * 32)
     ans_decode_plain_kernel(const uint32_t *__restrict__ table, const uint8_t *__restrict__ data,
                             uint64_t data_bytes, uint32_t n_groups, uint32_t n_lanes,
                             uint8_t *__restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t smem_s = smem_u32(smem);
-  trap_unless_aligned(smem_s, kRing);
+  const uint32_t smem_s = (smem_u32(smem) + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tab_s = smem_s + kPlainWarps * kRing;
   load_table(tab_s, table, threadIdx.x, kPlainWarps * 32);
