@@ -91,17 +91,29 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
   return d;
 }
-// signed byte j of w as int; byte pair (j, j+1) as a packed int16x2 word
+// signed byte j of w as int; byte pair (j, j+1) as a packed int16x2 word.  The scalar
+// extractions are dot products with a one-hot selector (IDP.4A / IDP.2A): they issue on the
+// FMA pipe, which idles in the wavelet, instead of PRMT / SHF on the saturated ALU pipe.
 template <int J>
 __device__ __forceinline__ int sext_byte(uint32_t w) {
-  return static_cast<int>(prmt<((8 | J) << 12) | ((8 | J) << 8) | ((8 | J) << 4) | J>(w, 0u));
+  int d;
+  asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(1u << (8 * J)), "r"(0));
+  return d;
 }
 template <int J>
 __device__ __forceinline__ uint32_t sext_byte_pair(uint32_t w) {
   return prmt<((8 | (J + 1)) << 12) | ((J + 1) << 8) | ((8 | J) << 4) | J>(w, 0u);
 }
-__device__ __forceinline__ int lo16(uint32_t w) { return static_cast<int>(prmt<0x9910>(w, 0u)); }
-__device__ __forceinline__ int hi16(uint32_t w) { return static_cast<int>(w) >> 16; }
+__device__ __forceinline__ int lo16(uint32_t w) {
+  int d;
+  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x0001u), "r"(0));
+  return d;
+}
+__device__ __forceinline__ int hi16(uint32_t w) {
+  int d;
+  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x0100u), "r"(0));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack16(int a, int b) {
   return __byte_perm(static_cast<uint32_t>(a), static_cast<uint32_t>(b), 0x5410);
 }
@@ -607,7 +619,7 @@ constexpr int kWaWarps = 4;
 constexpr int kWaSmem = kWaWarps * kWarpWork;  // 36864
 
 template <int RGB>
-__global__ void __launch_bounds__(kWaWarps * 32, 5) wavelet_assemble_kernel(const BatchParams p) {
+__global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(const BatchParams p) {
   extern __shared__ __align__(2048) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
