@@ -10,7 +10,10 @@ configs[3], a batch of 1024 2048x2048 textures per GPU; --config picks another).
 are reference-encoded .gst streams of seeded synthetic images (`--distinct` different images,
 tiled to the batch size); they are resident in HBM when the timed region starts.  The `e2e`
 figure runs the same workload through gst_decompress_host_batch with pinned HOST buffers:
-host packing, H2D, decode and D2H of every DXT1 block inside the timed region.
+host packing, H2D, decode and D2H of every DXT1 block inside the timed region (the shape of
+GenTC::DecompressDXT, and of what the CPU reference arm produces).  `e2e_resident` is the
+photos_sf shape: the same host buffers through gst_load_host_batch, textures left in device
+memory, one 16-byte probe per image read back.
 
 Prints ONE JSON line on rank 0.
 """
@@ -325,6 +328,37 @@ def main():
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
+    # ---- photos_sf shape: host .gst buffers -> textures resident in device memory ---------------
+    e2e_res = None
+    if not args.no_e2e:
+        probe = dec.pinned(16 * images)
+
+        def res_step():
+            check(lib().gst_load_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, d_out.ptr, d_out.nbytes))
+            # the step's result read: first and last block of every image (strided D2H)
+            dec.download_2d(probe, d_out, 8, images, src_pitch=8 * N, dst_pitch=16)
+            dec.download_2d(probe, d_out, 8, images, src_pitch=8 * N, dst_pitch=16, src_offset=8 * N - 8, dst_offset=8)
+
+        dec.memset(d_out, 0xEE)
+        res_step()
+        dec.sync()
+        got0 = dec.download(d_out, 8 * N, offset=0)
+        assert fx.matches_golden(got0, goldens[order[0]]), "resident e2e output differs"
+        gotl = dec.download(d_out, 8 * N, offset=(images - 1) * 8 * N)
+        assert fx.matches_golden(gotl, goldens[order[-1]]), "resident e2e output differs"
+        assert np.array_equal(probe.array[:8], got0[:8]) and np.array_equal(probe.array[-8:], gotl[-8:])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        dt, _ = reduce_job(dt, [])
+        e2e_res = {"value": texels_job * e2e_steps / dt / 1e9, "unit": "GTexel/s",
+                   "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(16 * images * world),
+                   "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
+                   "note": "host .gst -> DXT1 resident in device memory (LoadCompressedDXTs into a device buffer); "
+                           "16-byte probe per image read back"}
     clocks = sampler.stop()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------
@@ -353,6 +387,16 @@ def main():
         dom = max(alg, key=lambda k: per_call.get(k, 0.0))
         fused_bytes, fused_ms = alg[dom], per_call[dom]
         achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
+        # DRAM bytes per launch of that kernel, from the committed `ncu --set full` capture
+        # (profiles/traffic.json holds dram__bytes_read + dram__bytes_write per image of a given size)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            per_img = tj.get(f"{width}x{height}", {}).get(dom)
+            if per_img is not None:
+                traffic = float(per_img) * images
+        except Exception:
+            pass
         step_gbs = alg_bytes_rank / (ms_step * 1e-3) / 1e9
         line = {
             "metric": "decoded GTexel/s (.gst -> DXT1)", "value": texels_job / (ms_step * 1e-3) / 1e9,
@@ -368,12 +412,12 @@ def main():
                              "working set fits L2 (latency-bound config)",
                        "parity": f"{checked} distinct images + last checked bit-exact before timing"},
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                          "kernel_ms": fused_ms, "kernel_bytes": fused_bytes,
                          "step_achieved": step_gbs, "step_frac": step_gbs / peak,
                          "kernel_ms_all": per_call,
                          "kernel_alg_bytes": alg},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": lib().gst_launches_per_batch() * args.steps,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": lib().gst_launches_per_batch() * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

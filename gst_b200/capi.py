@@ -38,6 +38,7 @@ PROTOTYPES = {
     "gst_host_free": (_int, [_vp, _vp]),
     "gst_upload_async": (_int, [_vp, _vp, _vp, _vp, _sz]),
     "gst_download_async": (_int, [_vp, _vp, _vp, _vp, _sz]),
+    "gst_download_2d_async": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     "gst_memset_async": (_int, [_vp, _vp, _vp, _int, _sz]),
     "gst_event_record": (_int, [_vp, _vp, _pp]),
     "gst_event_wait": (_int, [_vp]),
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "gst_load_rgb_batch": (_int, [_vp, _hdr_p, _u32, _vp, _vp, _sz, _vp, _pp, _u32, _pp]),
     "gst_decompress_host": (_int, [_vp, _vp, _sz, _int, _vp, _sz]),
     "gst_decompress_host_batch": (_int, [_vp, _pp, C.POINTER(_sz), _u32, _u32, _int, _vp, _sz]),
+    "gst_load_host_batch": (_int, [_vp, _pp, C.POINTER(_sz), _u32, _u32, _int, _vp, _sz]),
     "gst_load_dxt_batch_tapped": (_int, [_vp, _hdr_p, _u32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "gst_normalize_frequencies": (_int, [C.POINTER(_u32), _u32, _u32, C.POINTER(_u32)]),
     "gst_ans_create": (_int, [_vp, C.POINTER(_u32), _u32, _u32, _pp]),

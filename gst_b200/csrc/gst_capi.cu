@@ -422,6 +422,15 @@ int gst_download_async(gst_ctx *ctx, void *stream, void *dst_host, const void *s
   return GST_OK;
 }
 
+int gst_download_2d_async(gst_ctx *ctx, void *stream, void *dst_host, size_t dst_pitch, const void *src_dev,
+                          size_t src_pitch, size_t width_bytes, size_t rows) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost,
+                                 static_cast<cudaStream_t>(stream)));
+  return GST_OK;
+}
+
 int gst_memset_async(gst_ctx *ctx, void *stream, void *dst_dev, int value, size_t bytes) {
   if (!ctx) return fail(GST_ERR_INVALID, "null context");
   DeviceGuard guard(ctx->device);
@@ -485,8 +494,11 @@ size_t gst_packed_size(const gst_header *hdrs, uint32_t n) {
   return L.total_cmp;
 }
 
-int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint8_t *dst, size_t dst_cap,
-                   gst_header *hdrs_out) {
+namespace {
+// The device input layout of LoadCompressedDXTs (codec/decoder.cpp:430-476, demo/photos_sf.cpp:753-795):
+// writes the offsets region (and, with copy_payload, the frequency tables and the payloads) to dst.
+int pack_impl(const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint8_t *dst, size_t dst_cap,
+              gst_header *hdrs_out, bool copy_payload, BatchLayout *L_out) {
   if (!gst_files || !lens || !dst || !hdrs_out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
   for (uint32_t i = 0; i < n; ++i) {
     int rc = gst_parse_header(gst_files[i], lens[i], &hdrs_out[i]);
@@ -495,7 +507,9 @@ int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t
   BatchLayout L;
   int rc = layout_batch(hdrs_out, n, &L);
   if (rc) return rc;
-  if (dst_cap < L.total_cmp) return fail(GST_ERR_SMALL, "packed batch needs %zu bytes, buffer has %zu", L.total_cmp, dst_cap);
+  if (L_out) *L_out = L;
+  const size_t need = copy_payload ? L.total_cmp : L.off_region;
+  if (dst_cap < need) return fail(GST_ERR_SMALL, "packed batch needs %zu bytes, buffer has %zu", need, dst_cap);
   uint32_t *out_off = reinterpret_cast<uint32_t *>(dst);
   uint32_t *in_off = out_off + 4 * n;
   memset(dst, 0, L.off_region);
@@ -507,10 +521,12 @@ int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t
     const uint32_t N = L.n_blocks;
     const uint32_t in_sz[4] = {h.y_cmp_sz, h.chroma_cmp_sz, h.palette_sz, h.indices_sz};
     const uint32_t out_sz[4] = {2 * N, 4 * N, h.palette_bytes, N};
-    const uint8_t *src = gst_files[i] + GST_HEADER_BYTES;
-    memcpy(freqs + static_cast<size_t>(i) * 2048, src, 2048);
-    const size_t body = static_cast<size_t>(in_sz[0]) + in_sz[1] + in_sz[2] + in_sz[3];
-    memcpy(payload + in_acc, src + 2048, body);
+    if (copy_payload) {
+      const uint8_t *src = gst_files[i] + GST_HEADER_BYTES;
+      memcpy(freqs + static_cast<size_t>(i) * 2048, src, 2048);
+      const size_t body = static_cast<size_t>(in_sz[0]) + in_sz[1] + in_sz[2] + in_sz[3];
+      memcpy(payload + in_acc, src + 2048, body);
+    }
     for (int s = 0; s < 4; ++s) {
       in_off[4 * i + s] = in_acc;
       out_off[4 * i + s] = out_acc;
@@ -519,6 +535,13 @@ int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t
     }
   }
   return GST_OK;
+}
+
+}  // namespace
+
+int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint8_t *dst, size_t dst_cap,
+                   gst_header *hdrs_out) {
+  return pack_impl(gst_files, lens, n, dst, dst_cap, hdrs_out, true, nullptr);
 }
 
 // ---- scratch ---------------------------------------------------------------------------
@@ -585,8 +608,24 @@ int gst_load_dxt_batch_tapped(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, 
 // into pinned staging (two buffers per stream, so packing page k+4 overlaps the transfers of
 // page k), then enqueues H2D -> decode -> D2H on its stream.  Staging lives in the context
 // and only grows.
+namespace {
+int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint32_t page, int mode,
+               uint8_t *out, size_t out_cap, bool out_on_device);
+}
+
 int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n,
                               uint32_t page, int mode, uint8_t *out, size_t out_cap) {
+  return host_batch(ctx, gst_files, lens, n, page, mode, out, out_cap, false);
+}
+
+int gst_load_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n,
+                        uint32_t page, int mode, void *out_dev, size_t out_cap) {
+  return host_batch(ctx, gst_files, lens, n, page, mode, static_cast<uint8_t *>(out_dev), out_cap, true);
+}
+
+namespace {
+int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint32_t page, int mode,
+               uint8_t *out, size_t out_cap, bool out_on_device) {
   if (!ctx || !gst_files || !lens || !out || n == 0) return fail(GST_ERR_INVALID, "null or empty argument");
   if (page == 0 || page > n) page = n;
   gst_header h0;
@@ -632,7 +671,7 @@ int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, con
           e = cudaHostAlloc(reinterpret_cast<void **>(&s.pinned[k]), s.cap_in, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in);
       }
-      if (e == cudaSuccess && per_image * page > s.cap_out) {
+      if (e == cudaSuccess && !out_on_device && per_image * page > s.cap_out) {
         e = cudaStreamSynchronize(stream);
         if (s.d_out) cudaFree(s.d_out);
         s.d_out = nullptr;
@@ -645,24 +684,32 @@ int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, con
       // the previous upload out of this staging buffer must have left the host
       e = cudaEventSynchronize(s.h2d_done[j]);
       if (e != cudaSuccess) return bail(GST_ERR_CUDA, "staging wait failed", e);
-      int prc = gst_pack_batch(gst_files + first, lens + first, cnt, s.pinned[j], s.cap_in, hdrs.data());
+      // pack the page into the pinned staging buffer (demo/photos_sf.cpp:753-806), one H2D copy.
+      // (DMA-ing every file from where it lies -- two copies per image -- was measured slower: the
+      // per-copy cost outweighs the saved host memcpy.)
+      BatchLayout L;
+      int prc = pack_impl(gst_files + first, lens + first, cnt, s.pinned[j], s.cap_in, hdrs.data(), true, &L);
       if (prc) {
         slot_rc[si] = prc;
         slot_err[si] = g_err;
         return;
       }
-      const size_t packed = gst_packed_size(hdrs.data(), cnt);
-      e = cudaMemcpyAsync(s.d_in, s.pinned[j], packed, cudaMemcpyHostToDevice, stream);
+      e = cudaMemcpyAsync(s.d_in, s.pinned[j], L.total_cmp, cudaMemcpyHostToDevice, stream);
       if (e == cudaSuccess) e = cudaEventRecord(s.h2d_done[j], stream);
       if (e != cudaSuccess) return bail(GST_ERR_CUDA, "upload failed", e);
-      prc = decode_batch(ctx, hdrs.data(), cnt, stream, s.d_in, s.cap_in, s.d_out, mode, Taps{}, nullptr, 0, nullptr);
+      // the textures either stay in the caller's device buffer (LoadCompressedDXTs into a PBO,
+      // demo/photos_sf.cpp:810-821) or come back to the host (DecompressDXT)
+      prc = decode_batch(ctx, hdrs.data(), cnt, stream, s.d_in, s.cap_in, out_on_device ? out + per_image * first : s.d_out,
+                         mode, Taps{}, nullptr, 0, nullptr);
       if (prc) {
         slot_rc[si] = prc;
         slot_err[si] = g_err;
         return;
       }
-      e = cudaMemcpyAsync(out + per_image * first, s.d_out, per_image * cnt, cudaMemcpyDeviceToHost, stream);
-      if (e != cudaSuccess) return bail(GST_ERR_CUDA, "download failed", e);
+      if (!out_on_device) {
+        e = cudaMemcpyAsync(out + per_image * first, s.d_out, per_image * cnt, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return bail(GST_ERR_CUDA, "download failed", e);
+      }
     }
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) bail(GST_ERR_CUDA, "decode failed", e);
@@ -680,6 +727,7 @@ int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, con
     if (slot_rc[si]) return fail(slot_rc[si], "%s", slot_err[si].c_str());
   return GST_OK;
 }
+}  // namespace
 
 int gst_decompress_host(gst_ctx *ctx, const uint8_t *gst, size_t len, int mode, uint8_t *out, size_t out_cap) {
   const uint8_t *files[1] = {gst};

@@ -259,6 +259,14 @@ class Decoder:
             self.sync(s)
         return out
 
+    def download_2d(self, pinned, dbuf, width, rows, src_pitch, dst_pitch, src_offset=0, dst_offset=0, stream=None):
+        """rows x width bytes, strided on both sides, into a PinnedBuffer (blocking unless a stream is given)."""
+        s = stream if stream is not None else self.GetDefaultCommandQueue()
+        check(lib().gst_download_2d_async(self.ctx, s, pinned.ptr + dst_offset, dst_pitch, dbuf.ptr + src_offset,
+                                          src_pitch, width, rows))
+        if stream is None:
+            self.sync(s)
+
     def memset(self, dbuf, value, stream=None):
         s = stream if stream is not None else self.GetDefaultCommandQueue()
         check(lib().gst_memset_async(self.ctx, s, dbuf.ptr, int(value), dbuf.nbytes))
@@ -335,6 +343,14 @@ class Decoder:
         lens = (C.c_size_t * n)(*[a.size for a in arrs])
         check(lib().gst_decompress_host_batch(self.ctx, ptrs, lens, n, int(page), int(mode), out.ctypes.data, out.size))
         return out
+
+    def LoadHostBatch(self, files, output, page=16, mode=0):
+        """The headless photos_sf loader (demo/photos_sf.cpp:688-885): host .gst buffers (numpy
+        arrays or PinnedBuffers) -> textures in the caller's DeviceBuffer `output`."""
+        n = len(files)
+        ptrs = (C.c_void_p * n)(*[f.ptr if isinstance(f, PinnedBuffer) else _as_u8(f).ctypes.data for f in files])
+        lens = (C.c_size_t * n)(*[f.nbytes if isinstance(f, PinnedBuffer) else _as_u8(f).size for f in files])
+        check(lib().gst_load_host_batch(self.ctx, ptrs, lens, n, int(page), int(mode), output.ptr, output.nbytes))
 
     def decode_tapped(self, files):
         """Decode a batch and also return the stage intermediates (parity tests):

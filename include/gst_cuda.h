@@ -75,6 +75,9 @@ int gst_host_alloc(gst_ctx *ctx, size_t bytes, void **hptr);
 int gst_host_free(gst_ctx *ctx, void *hptr);
 int gst_upload_async(gst_ctx *ctx, void *stream, void *dst_dev, const void *src_host, size_t bytes);
 int gst_download_async(gst_ctx *ctx, void *stream, void *dst_host, const void *src_dev, size_t bytes);
+/* strided read-back (rows of width_bytes): e.g. one block of every texture of a batch */
+int gst_download_2d_async(gst_ctx *ctx, void *stream, void *dst_host, size_t dst_pitch,
+                          const void *src_dev, size_t src_pitch, size_t width_bytes, size_t rows);
 int gst_memset_async(gst_ctx *ctx, void *stream, void *dst_dev, int value, size_t bytes);
 
 /* ---- events: replace cl_event hand-off (codec/decoder.h:19-33).  The caller owns every
@@ -131,6 +134,14 @@ int gst_decompress_host(gst_ctx *ctx, const uint8_t *gst, size_t len, int mode, 
  * streams in pages of `page` images (demo/photos_sf.cpp:688 kPageSize = 16; 0 = one page). */
 int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens,
                               uint32_t n, uint32_t page, int mode, uint8_t *out, size_t out_cap);
+
+/* The headless form of the photos_sf loader (demo/photos_sf.cpp:688-885): n .gst files in host
+ * memory are packed page by page into pinned staging on the context's worker threads, copied
+ * to the device and decoded with LoadCompressedDXTs semantics straight into the caller's DEVICE
+ * buffer out_dev (image i at i * W*H/2 bytes, or i * W*H*3 in RGB mode) -- where the reference
+ * hands the pages to a GL pixel buffer.  Blocking; pages overlap across the work streams. */
+int gst_load_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens,
+                        uint32_t n, uint32_t page, int mode, void *out_dev, size_t out_cap);
 
 /* ---- stage taps for the parity tests (not used in production).  Any pointer may be NULL.
  *   symbols_dev : sum(7N + P) bytes, reference decmp_buf layout (codec/decoder.cpp:212)

@@ -169,3 +169,64 @@ def test_deterministic(decoder):
     a = decoder.DecompressDXTs([gst] * 8, page=8)
     b = decoder.DecompressDXTs([gst] * 8, page=3)
     assert np.array_equal(a, b)
+
+
+def test_config1_batch_128_small_textures(decoder):
+    """BASELINE.json configs[1]: a batch of 128 512x512 textures in ONE call (the photos_sf layout,
+    demo/photos_sf.cpp:753-795, with all 128 in a single page): 8 distinct reference-encoded images
+    tiled, every output equal to the encoder's PhysicalBlocks() of its source."""
+    srcs = [fx.encode_image(512, 512, 10000 + i) for i in range(8)]
+    order = [(5 * i + 3) % 8 for i in range(128)]
+    out = decoder.DecompressDXTs([srcs[j][0] for j in order], page=128)
+    per = 512 * 512 // 2
+    for pos, j in enumerate(order):
+        assert np.array_equal(out[pos * per:(pos + 1) * per], srcs[j][1]), f"image {pos}"
+    assert np.array_equal(out[:per], fx.oracle_decode(srcs[order[0]][0], taps=False)["out"])
+
+
+def test_config4_frame_sequence_streamed(decoder):
+    """BASELINE.json configs[4]: a 1920x1024 frame sequence streamed one frame per page through
+    the work streams (demo/demo.cpp:145-243 decodes frameNNNN.gtc one at a time); frames cycle
+    over 3 distinct reference-encoded images, outputs stay in device memory and are read back
+    once at the end."""
+    srcs = [fx.encode_image(1920, 1024, 40000 + i) for i in range(3)]
+    n = 24
+    order = [i % 3 for i in range(n)]
+    per = 1920 * 1024 // 2
+    d_out = decoder.malloc(per * n)
+    decoder.memset(d_out, 0xEE)
+    pins = []
+    for g, _ in srcs:
+        pb = decoder.pinned(g.size)
+        pb.array[:] = g
+        pins.append(pb)
+    decoder.LoadHostBatch([pins[j] for j in order], d_out, page=1)
+    got = decoder.download(d_out)
+    for pos, j in enumerate(order):
+        assert fx.matches_golden(got[pos * per:(pos + 1) * per], srcs[j][1]), f"frame {pos}"
+    d_out.free()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_load_host_batch_resident(decoder, pinned):
+    """gst_load_host_batch with pageable and with page-locked sources: identical textures on the
+    device, ragged last page included."""
+    srcs = [fx.encode_image(512, 512, 10000 + i) for i in range(4)] + [(fx.golden_test1())]
+    order = [(3 * i) % 5 for i in range(23)]  # ragged last page
+    files = []
+    for j in order:
+        g = srcs[j][0]
+        if pinned:
+            pb = decoder.pinned(g.size)
+            pb.array[:] = g
+            files.append(pb)
+        else:
+            files.append(g)
+    per = 512 * 512 // 2
+    d_out = decoder.malloc(per * len(order))
+    decoder.memset(d_out, 0x55)
+    decoder.LoadHostBatch(files, d_out, page=4)
+    got = decoder.download(d_out)
+    for pos, j in enumerate(order):
+        assert np.array_equal(got[pos * per:(pos + 1) * per], srcs[j][1]), f"image {pos}"
+    d_out.free()
