@@ -632,12 +632,14 @@ __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(cons
   const uint32_t tile = gt_tile % tiles_per_image;
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
-  const ImageStreams is = image_streams(p, b);
+  // out_off[4b..4b+3] of this image (codec/decoder.cpp:430-463): requested now, first used after
+  // the first plane pair, so the warp never waits for it
+  const uint4 out_off = __ldg(reinterpret_cast<const uint4 *>(p.cmp) + b);
+  uint32_t n_entries = 0;
+  bool pal_ok = false;
+  const uint32_t *pal = nullptr;
 
   // ---- assembly inputs of slab 0 start their trip now ---------------------------------
-  const uint32_t n_entries = is.palette_bytes / 4;
-  const bool pal_ok = static_cast<uint64_t>(is.pal_off) + is.palette_bytes <= p.palette_cap && n_entries > 0;
-  const uint32_t *pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? is.pal_off : 0));
   const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
   const int32_t *run_end = p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane);
   const bool idx16 = p.idx16 != 0;
@@ -782,6 +784,11 @@ __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(cons
       __syncwarp();
     }
     if (pair == 0) {  // slab 0: indices -> palette words;  slabs 1, 2: suffix sums in flight
+      const uint32_t palette_bytes = out_off.w - out_off.z;
+      const uint32_t pal_off = out_off.z - 7u * p.n_blocks * b - 6u * p.n_blocks;  // compact palette scratch
+      n_entries = palette_bytes / 4;
+      pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
+      pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? pal_off : 0));
       load_words(sa, gidx0);
       sa = sb;
       sb = load_sfx(gidx0 + 2 * slab_stride);
