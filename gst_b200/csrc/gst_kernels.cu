@@ -149,87 +149,108 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// emit(m, w0, w1, w2, w3): called 16 times; the 16 symbols at positions q0 = 240 - 16m .. q0 + 15
-// of this lane's 256-symbol run, little-endian packed (w0 = q0..q0+3, ..., w3 = q0+12..q0+15).
-template <bool FULL, class Emit>
-__device__ __forceinline__ void rans_decode_group(uint32_t tab_s, const uint8_t *__restrict__ stream,
-                                                  uint32_t group, uint32_t n_lanes, uint32_t ring_s,
-                                                  const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
+// NC = 1 or 2 groups per warp.  With NC = 2 the warp decodes groups `group` and `group + 1` of the
+// same stream in one interleaved instruction stream: the decode step is a chain of ~14 dependent
+// instructions (two of them shared-memory loads), and two independent chains per warp hide
+// that latency better than twice the warps would (registers, not warps, are what is left).
+// Chain c uses the ring at ring_s + c * kRing.
+// emit(c, m, w0, w1, w2, w3): called 16 times per chain; the 16 symbols at positions
+// q0 = 240 - 16m .. q0 + 15 of this lane's 256-symbol run of chain c, little-endian packed
+// (w0 = q0..q0+3, ..., w3 = q0+12..q0+15).
+template <bool FULL, int NC, class Emit>
+__device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t *__restrict__ stream,
+                                                   uint32_t group, uint32_t n_lanes, uint32_t ring_s,
+                                                   const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gt = lanemask_gt();
   const bool active = FULL || lane < n_lanes;
-
-  // ans/ans_decode.cl:30.  Clamp so a malformed offset can never leave [buf_lo, buf_hi).
-  const uint32_t end = __ldg(reinterpret_cast<const uint32_t *>(stream) + group) & ~3u;
-  uintptr_t top = reinterpret_cast<uintptr_t>(stream) + end;
   const uintptr_t lo_ok = reinterpret_cast<uintptr_t>(buf_lo) + 4 * n_lanes;
   const uintptr_t hi_ok = reinterpret_cast<uintptr_t>(buf_hi) & ~static_cast<uintptr_t>(3);
-  top = top < lo_ok ? lo_ok : top;
-  top = top > hi_ok ? hi_ok : top;
-  const uintptr_t a_pos = top - 4 * n_lanes;  // one past the last renorm word
-
-  // ans/ans_decode.cl:31
-  uint32_t state = active ? __ldg(reinterpret_cast<const uint32_t *>(a_pos) + lane) : 0u;
-
-  // preload [c_top - 2048, c_top), c_top = a_pos rounded up to 512
   const uintptr_t lo16 = (reinterpret_cast<uintptr_t>(buf_lo) + 15) & ~static_cast<uintptr_t>(15);
   const uintptr_t hi16 = reinterpret_cast<uintptr_t>(buf_hi) & ~static_cast<uintptr_t>(15);
-  const uintptr_t c_top = (a_pos + (kChunk - 1)) & ~static_cast<uintptr_t>(kChunk - 1);
-  uintptr_t lo = c_top - kRing;
+
+  uint32_t state[NC], cur2[NC];
+  uintptr_t lo[NC];
+  uint32_t end[NC];
 #pragma unroll
-  for (int i = 0; i < kRing / kChunk; ++i) {
-    const uintptr_t a = lo + 16 * lane + kChunk * i;
-    if (a >= lo16 && a + 16 <= hi16) cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+  for (int c = 0; c < NC; ++c) end[c] = __ldg(reinterpret_cast<const uint32_t *>(stream) + group + c) & ~3u;  // ans/ans_decode.cl:30
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    // Clamp so a malformed offset can never leave [buf_lo, buf_hi).
+    uintptr_t top = reinterpret_cast<uintptr_t>(stream) + end[c];
+    top = top < lo_ok ? lo_ok : top;
+    top = top > hi_ok ? hi_ok : top;
+    const uintptr_t a_pos = top - 4 * n_lanes;  // one past the last renorm word
+    // ans/ans_decode.cl:31
+    state[c] = active ? __ldg(reinterpret_cast<const uint32_t *>(a_pos) + lane) : 0u;
+    // preload [c_top - kRing, c_top), c_top = a_pos rounded up to kChunk
+    const uintptr_t c_top = (a_pos + (kChunk - 1)) & ~static_cast<uintptr_t>(kChunk - 1);
+    lo[c] = c_top - kRing;
+#pragma unroll
+    for (int i = 0; i < kRing / kChunk; ++i) {
+      const uintptr_t a = lo[c] + 16 * lane + kChunk * i;
+      if (a >= lo16 && a + 16 <= hi16)
+        cp_async16(ring_s + c * kRing + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+    }
+    cur2[c] = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
   }
   cp_async_commit();
   cp_async_wait_group<0>();
   __syncwarp();
 
-  uint32_t cur2 = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
-
 #pragma unroll 1
   for (int m = 0; m < 16; ++m) {
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    uint32_t acc[NC][4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      // checkpoint: top up when < 1536 B are staged, then let the two newest groups fly
-      if (cur2 + 2u - static_cast<uint32_t>(lo) < static_cast<uint32_t>(kRing - kChunk)) {
-        lo -= kChunk;
-        const uintptr_t a = lo + 16 * lane;
-        if (a >= lo16 && a + 16 <= hi16) cp_async16(ring_s + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+      // checkpoint: top up when < kRing - kChunk bytes are staged, then let the two newest groups fly
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (cur2[c] + 2u - static_cast<uint32_t>(lo[c]) < static_cast<uint32_t>(kRing - kChunk)) {
+          lo[c] -= kChunk;
+          const uintptr_t a = lo[c] + 16 * lane;
+          if (a >= lo16 && a + 16 <= hi16)
+            cp_async16(ring_s + c * kRing + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+        }
       }
       cp_async_commit();
       cp_async_wait_group<2>();
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        uint32_t slot_a;  // tab_s + 4 * (state & 2047)
-        asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(state & (kTableSize - 1)), "r"(tab_s));
-        const uint32_t e = lds32(slot_a);
-        // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  Written as multiplies so
-        // that the shifts issue on the FMA pipe: the ALU pipe (LOP3 / PRMT / ISETP) is the busy one.
-        uint32_t f21, sym24, hi;
-        int32_t bias;
-        asm("mul.lo.u32 %0, %1, 2097152;" : "=r"(f21) : "r"(e));   // e << 21
-        asm("mul.hi.s32 %0, %1, 8192;" : "=r"(bias) : "r"(e));     // (int)e >> 19
-        asm("mul.lo.u32 %0, %1, 8192;" : "=r"(sym24) : "r"(e));    // e << 13: symbol in the top byte
-        asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(state), "r"(f21));
-        state = hi + static_cast<uint32_t>(bias);
-        const bool need = FULL ? (state < kRansL) : (active && state < kRansL);
-        const uint32_t mask = __ballot_sync(0xffffffffu, need);
-        const uint32_t a = cur2 - 2u * __popc(mask & gt);
-        uint32_t ra;  // ring_s | (a & (kRing - 1)) in one LOP3 (the ring is kRing-aligned)
-        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(a), "n"(kRing - 1), "r"(ring_s));  // (a & mask) | ring
-        const uint32_t w = lds_u16(ra);
-        uint32_t renorm;  // state << 16 | w
-        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state), "r"(w));
-        if (need) state = renorm;
-        cur2 -= 2u * __popc(mask);                              // ans/ans_decode.cl:65
-        const int word = 3 - 2 * h - (k >> 2);
-        acc[word] = __byte_perm(acc[word], sym24, 0x2107);      // acc << 8 | symbol
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t slot_a;  // tab_s + 4 * (state & 2047)
+          asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(state[c] & (kTableSize - 1)), "r"(tab_s));
+          const uint32_t e = lds32(slot_a);
+          // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  Written as multiplies so
+          // that the shifts issue on the FMA pipe: the ALU pipe (LOP3 / PRMT / ISETP) is the busy one.
+          uint32_t f21, sym24, hi;
+          int32_t bias;
+          asm("mul.lo.u32 %0, %1, 2097152;" : "=r"(f21) : "r"(e));   // e << 21
+          asm("mul.hi.s32 %0, %1, 8192;" : "=r"(bias) : "r"(e));     // (int)e >> 19
+          asm("mul.lo.u32 %0, %1, 8192;" : "=r"(sym24) : "r"(e));    // e << 13: symbol in the top byte
+          asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(state[c]), "r"(f21));
+          state[c] = hi + static_cast<uint32_t>(bias);
+          const bool need = FULL ? (state[c] < kRansL) : (active && state[c] < kRansL);
+          const uint32_t mask = __ballot_sync(0xffffffffu, need);
+          const uint32_t a = cur2[c] - 2u * __popc(mask & gt);
+          uint32_t ra;  // (a & (kRing - 1)) | ring in one LOP3 (the ring is kRing-aligned)
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(a), "n"(kRing - 1), "r"(ring_s + c * kRing));
+          const uint32_t w = lds_u16(ra);
+          uint32_t renorm;  // state << 16 | w
+          asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state[c]), "r"(w));
+          if (need) state[c] = renorm;
+          cur2[c] -= 2u * __popc(mask);                                 // ans/ans_decode.cl:65
+          const int word = 3 - 2 * h - (k >> 2);
+          acc[c][word] = __byte_perm(acc[c][word], sym24, 0x2107);      // acc << 8 | symbol
+        }
       }
     }
-    emit(m, acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) emit(c, m, acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
   }
   cp_async_wait_group<0>();
 }
@@ -358,7 +379,9 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 //       difference exact), else as 32 bits, in the same transposed order as sym_t:
 //       [group][k][lane][16 values].
 constexpr int kRansWarps = 8;
-constexpr int kRansSmem = kRansWarps * kRing + kTableSize * 4 + kRing;  // + alignment slack
+constexpr int kRansChains = 2;                          // rANS groups per warp
+constexpr int kRansGroupsPerCta = kRansWarps * kRansChains;
+constexpr int kRansSmem = kRansGroupsPerCta * kRing + kTableSize * 4 + kRing;  // + alignment slack
 
 // CTAs of one image: [Y][chroma][palette][index]
 struct StreamGrid {
@@ -366,14 +389,89 @@ struct StreamGrid {
   __host__ __device__ uint32_t per_image() const { return y_ctas + c_ctas + pal_ctas + idx_ctas; }
 };
 
-__global__ void __launch_bounds__(kRansWarps * 32, 8) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+// One warp's share of a stream: NC consecutive groups starting at `group`.
+template <int NC>
+__device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_t b, uint32_t type, uint32_t group,
+                                                   const uint8_t *stream, uint32_t out_off, uint32_t pal_off,
+                                                   uint32_t tab_s, uint32_t ring_s) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint8_t *tap = p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 240
+                               : nullptr;
+  if (type < 2) {
+    const size_t pg = (type ? 2 * p.groups_per_plane : 0) + group;
+    uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + pg * kGroupSyms + 15 * 512 + lane * 16;
+    rans_decode_groups<true, NC>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                                 [&](int c, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                                   *reinterpret_cast<uint4 *>(dst + c * kGroupSyms - 512 * m) = make_uint4(w0, w1, w2, w3);
+                                   if (tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
+                                 });
+    return;
+  }
+  if (type == 2) {
+    const uint64_t off = static_cast<uint64_t>(pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
+    const bool ok = off + NC * kGroupSyms <= p.palette_cap;
+    uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
+    rans_decode_groups<true, NC>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                                 [&](int c, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                                   if (ok) *reinterpret_cast<uint4 *>(dst + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
+                                   if (tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
+                                 });
+    return;
+  }
+
+  uint32_t sum[NC];  // sum of (byte - 128) over the symbols decoded so far = positions after the current one
+#pragma unroll
+  for (int c = 0; c < NC; ++c) sum[c] = 0;
+  const size_t t0 = static_cast<size_t>(b) * p.n_blocks + static_cast<size_t>(group) * kGroupSyms + 15 * 512 + lane * 16;
+  uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
+  uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
+  const bool idx16 = p.idx16 != 0;
+  rans_decode_groups<true, NC>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                               [&](int c, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                                 if (tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
+                                 const uint32_t w[4] = {w0, w1, w2, w3};
+                                 uint32_t s[16];
+#pragma unroll
+                                 for (int i = 15; i >= 0; --i) {
+                                   s[i] = sum[c];
+                                   sum[c] += ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 128u;
+                                 }
+                                 if (idx16) {
+                                   uint32_t q[8];
+#pragma unroll
+                                   for (int i = 0; i < 8; ++i) q[i] = __byte_perm(s[2 * i], s[2 * i + 1], 0x5410);
+                                   uint16_t *d = dst16 + c * kGroupSyms - 512 * m;
+                                   *reinterpret_cast<uint4 *>(d) = make_uint4(q[0], q[1], q[2], q[3]);
+                                   *reinterpret_cast<uint4 *>(d + 8) = make_uint4(q[4], q[5], q[6], q[7]);
+                                 } else {
+                                   uint32_t *d = dst32 + c * kGroupSyms - 512 * m;
+#pragma unroll
+                                   for (int i = 0; i < 4; ++i)
+                                     *reinterpret_cast<uint4 *>(d + 4 * i) = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+                                 }
+                               });
+  // group-local inclusive prefix at the end of every run, and the group total
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t inc = sum[c];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += n;
+    }
+    p.run_end[static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + (group + c) * kLanes + lane] = static_cast<int32_t>(inc);
+    if (lane == 31) p.idx_total[static_cast<size_t>(b) * p.groups_per_plane + group + c] = static_cast<int32_t>(inc);
+  }
+}
+
+__global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // the rings are indexed by OR-ing low address bits, so they must be kRing-aligned; the dynamic
   // shared window itself is only guaranteed 1 KiB alignment, hence kRing bytes of slack
   const uint32_t smem_s = (smem_u32(smem) + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ring_s = smem_s + warp * kRing;
-  const uint32_t tab_s = smem_s + kRansWarps * kRing;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t ring_s = smem_s + warp * kRansChains * kRing;
+  const uint32_t tab_s = smem_s + kRansGroupsPerCta * kRing;
 
   const uint32_t per_image = sg.per_image();
   const uint32_t b = blockIdx.x / per_image;
@@ -386,79 +484,21 @@ __global__ void __launch_bounds__(kRansWarps * 32, 8) rans_streams_kernel(const 
   const ImageStreams is = image_streams(p, b);
   const uint32_t n_groups = type == 0 ? 2 * p.groups_per_plane : type == 1 ? 4 * p.groups_per_plane
                           : type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
-  const uint32_t first = r * kRansWarps;
+  const uint32_t first = r * kRansGroupsPerCta;
   if (first >= n_groups) return;
 
   load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
   __syncthreads();
-  const uint32_t group = first + warp;
+  const uint32_t group = first + warp * kRansChains;
   if (group >= n_groups) return;
   // in_off[type] / out_off[type] by selection (a dynamically indexed array would live in local memory)
   const uint32_t in_off = type == 0 ? is.in_off[0] : type == 1 ? is.in_off[1] : type == 2 ? is.in_off[2] : is.in_off[3];
   const uint32_t out_off = type == 0 ? is.out_off[0] : type == 1 ? is.out_off[1] : type == 2 ? is.out_off[2] : is.out_off[3];
   const uint8_t *stream = is.payload + in_off;
-  uint8_t *tap = p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 240
-                               : nullptr;
-
-  if (type < 2) {
-    const size_t pg = (type ? 2 * p.groups_per_plane : 0) + group;
-    uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + pg * kGroupSyms + 15 * 512 + lane * 16;
-    rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                            [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                              *reinterpret_cast<uint4 *>(dst - 512 * m) = make_uint4(w0, w1, w2, w3);
-                              if (tap) *reinterpret_cast<uint4 *>(tap - 16 * m) = make_uint4(w0, w1, w2, w3);
-                            });
-    return;
-  }
-  if (type == 2) {
-    const uint64_t off = static_cast<uint64_t>(is.pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
-    const bool ok = off + kGroupSyms <= p.palette_cap;
-    uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
-    rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                            [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                              if (ok) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w0, w1, w2, w3);
-                              if (tap) *reinterpret_cast<uint4 *>(tap - 16 * m) = make_uint4(w0, w1, w2, w3);
-                            });
-    return;
-  }
-
-  uint32_t sum = 0;  // sum of (byte - 128) over the symbols decoded so far = positions after the current one
-  const size_t t0 = static_cast<size_t>(b) * p.n_blocks + static_cast<size_t>(group) * kGroupSyms + 15 * 512 + lane * 16;
-  uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
-  uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
-  const bool idx16 = p.idx16 != 0;
-  rans_decode_group<true>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                          [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                            if (tap) *reinterpret_cast<uint4 *>(tap - 16 * m) = make_uint4(w0, w1, w2, w3);
-                            const uint32_t w[4] = {w0, w1, w2, w3};
-                            uint32_t s[16];
-#pragma unroll
-                            for (int i = 15; i >= 0; --i) {
-                              s[i] = sum;
-                              sum += ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 128u;
-                            }
-                            if (idx16) {
-                              uint32_t q[8];
-#pragma unroll
-                              for (int i = 0; i < 8; ++i) q[i] = __byte_perm(s[2 * i], s[2 * i + 1], 0x5410);
-                              *reinterpret_cast<uint4 *>(dst16 - 512 * m) = make_uint4(q[0], q[1], q[2], q[3]);
-                              *reinterpret_cast<uint4 *>(dst16 - 512 * m + 8) = make_uint4(q[4], q[5], q[6], q[7]);
-                            } else {
-#pragma unroll
-                              for (int i = 0; i < 4; ++i)
-                                *reinterpret_cast<uint4 *>(dst32 - 512 * m + 4 * i) =
-                                    make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
-                            }
-                          });
-  // group-local inclusive prefix at the end of every run, and the group total
-  uint32_t inc = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += n;
-  }
-  p.run_end[static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + group * kLanes + lane] = static_cast<int32_t>(inc);
-  if (lane == 31) p.idx_total[static_cast<size_t>(b) * p.groups_per_plane + group] = static_cast<int32_t>(inc);
+  if (group + 1 < n_groups)
+    rans_stream_groups<2>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
+  else
+    rans_stream_groups<1>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
 }
 
 // The cross-group part of stage 3 (what the collect_indices passes of
@@ -901,8 +941,8 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
   if (group >= n_groups) return;
   uint8_t *dst = out + (static_cast<size_t>(group) * n_lanes + lane) * kSymsPerLane + 240;
   const bool active = lane < n_lanes;
-  rans_decode_group<false>(tab_s, data, group, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
-                           [&](int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  rans_decode_groups<false, 1>(tab_s, data, group, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
+                           [&](int, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
                              if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w0, w1, w2, w3);
                            });
 }
@@ -945,10 +985,10 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
   StreamGrid sg;
-  sg.y_ctas = (2 * p.groups_per_plane + kRansWarps - 1) / kRansWarps;
-  sg.c_ctas = (4 * p.groups_per_plane + kRansWarps - 1) / kRansWarps;
-  sg.pal_ctas = (max_palette_bytes / kGroupSyms + kRansWarps - 1) / kRansWarps;
-  sg.idx_ctas = (p.groups_per_plane + kRansWarps - 1) / kRansWarps;
+  sg.y_ctas = (2 * p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
+  sg.c_ctas = (4 * p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
+  sg.pal_ctas = (max_palette_bytes / kGroupSyms + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
+  sg.idx_ctas = (p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
   rans_streams_kernel<<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
