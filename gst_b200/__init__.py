@@ -9,6 +9,7 @@ from .capi import GstError, lib, load_library  # noqa: F401
 from .decoder import (  # noqa: F401
     AnsDecoder,
     Decoder,
+    FrameStreamer,
     GenTCHeader,
     kANSTableSize,
     kNumEncodedSymbols,
@@ -21,7 +22,7 @@ from .decoder import (  # noqa: F401
 )
 
 __all__ = [
-    "AnsDecoder", "Decoder", "GenTCHeader", "GstError", "lib", "load_library",
+    "AnsDecoder", "Decoder", "FrameStreamer", "GenTCHeader", "GstError", "lib", "load_library",
     "normalize_frequencies", "pack_batch", "parse_header", "required_scratch_mem",
     "kANSTableSize", "kNumEncodedSymbols", "kThreadsPerEncodingGroup", "kWaveletBlockDim",
 ]

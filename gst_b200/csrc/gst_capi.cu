@@ -77,6 +77,26 @@ struct gst_ans_decoder {
   uint8_t *freqs = nullptr;   // device, 512 B
 };
 
+// Frame streamer: `depth` frames in flight, each slot owns pinned staging, a device input, a
+// device output, a stream and a completion event (demo/demo.cpp:145-243 keeps ONE frame in flight
+// and blocks on its event, :221).
+struct gst_streamer {
+  gst_ctx *ctx = nullptr;
+  uint32_t width = 0, height = 0, depth = 0;
+  int mode = 0;
+  size_t frame_bytes = 0;  // decoded bytes per frame
+  uint64_t next_ticket = 0;
+  struct Slot {
+    uint8_t *pinned = nullptr, *d_in = nullptr, *d_out = nullptr;
+    size_t cap_in = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint64_t ticket = UINT64_MAX;  // frame currently (or last) in the slot
+    void *frame_dev = nullptr;     // where that frame was decoded to
+  };
+  std::vector<Slot> slots;
+};
+
 namespace {
 
 using HostSlot = gst_ctx::HostSlotT;
@@ -733,6 +753,104 @@ int gst_decompress_host(gst_ctx *ctx, const uint8_t *gst, size_t len, int mode, 
   const uint8_t *files[1] = {gst};
   const size_t lens[1] = {len};
   return gst_decompress_host_batch(ctx, files, lens, 1, 1, mode, out, out_cap);
+}
+
+// ---- frame streamer ---------------------------------------------------------------------
+int gst_streamer_create(gst_ctx *ctx, uint32_t width, uint32_t height, uint32_t depth, int mode, gst_streamer **out) {
+  if (!ctx || !out) return fail(GST_ERR_INVALID, "null argument");
+  if (depth == 0 || depth > 64) return fail(GST_ERR_INVALID, "depth must be 1..64");
+  gst_header h{};
+  h.width = width;
+  h.height = height;
+  int rc = check_header(h);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  gst_streamer *st = new (std::nothrow) gst_streamer;
+  if (!st) return fail(GST_ERR_NOMEM, "out of host memory");
+  st->ctx = ctx;
+  st->width = width;
+  st->height = height;
+  st->depth = depth;
+  st->mode = mode ? 1 : 0;
+  st->frame_bytes = mode ? static_cast<size_t>(width) * height * 3 : static_cast<size_t>(width) * height / 2;
+  st->slots.resize(depth);
+  for (auto &s : st->slots) {
+    cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_out), st->frame_bytes);
+    if (e != cudaSuccess) {
+      gst_streamer_destroy(st);
+      return fail(GST_ERR_CUDA, "streamer allocation failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = st;
+  return GST_OK;
+}
+
+void gst_streamer_destroy(gst_streamer *st) {
+  if (!st) return;
+  DeviceGuard guard(st->ctx->device);
+  for (auto &s : st->slots) {
+    if (s.stream) {
+      cudaStreamSynchronize(s.stream);
+      cudaStreamDestroy(s.stream);
+    }
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.pinned) cudaFreeHost(s.pinned);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+  }
+  delete st;
+}
+
+int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, uint64_t *ticket) {
+  if (!st || !gst) return fail(GST_ERR_INVALID, "null argument");
+  gst_header h;
+  int rc = gst_parse_header(gst, len, &h);
+  if (rc) return rc;
+  if (h.width != st->width || h.height != st->height)
+    return fail(GST_ERR_INVALID, "frame is %ux%u, the streamer was created for %ux%u", h.width, h.height, st->width, st->height);
+  DeviceGuard guard(st->ctx->device);
+  const uint64_t t = st->next_ticket;
+  gst_streamer::Slot &s = st->slots[t % st->depth];
+  // the slot's previous frame (ticket t - depth) must have been decoded: its staging is reused
+  if (s.ticket != UINT64_MAX) GST_CUDA_TRY(cudaEventSynchronize(s.done));
+  const size_t need = kQuantum + len;  // offsets region + everything after the header
+  if (need > s.cap_in) {
+    if (s.pinned) cudaFreeHost(s.pinned);
+    if (s.d_in) cudaFree(s.d_in);
+    s.pinned = s.d_in = nullptr;
+    s.cap_in = align_up(need + need / 2, 4096);
+    GST_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s.pinned), s.cap_in, cudaHostAllocDefault));
+    GST_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in));
+  }
+  const uint8_t *files[1] = {gst};
+  const size_t lens[1] = {len};
+  BatchLayout L;
+  rc = pack_impl(files, lens, 1, s.pinned, s.cap_in, &h, true, &L);  // demo/demo.cpp:165-192
+  if (rc) return rc;
+  GST_CUDA_TRY(cudaMemcpyAsync(s.d_in, s.pinned, L.total_cmp, cudaMemcpyHostToDevice, s.stream));
+  void *dst = out_dev ? out_dev : s.d_out;
+  rc = decode_batch(st->ctx, &h, 1, s.stream, s.d_in, s.cap_in, dst, st->mode, Taps{}, nullptr, 0, nullptr);
+  if (rc) return rc;
+  GST_CUDA_TRY(cudaEventRecord(s.done, s.stream));
+  s.ticket = t;
+  s.frame_dev = dst;
+  st->next_ticket = t + 1;
+  if (ticket) *ticket = t;
+  return GST_OK;
+}
+
+int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev) {
+  if (!st) return fail(GST_ERR_INVALID, "null streamer");
+  gst_streamer::Slot &s = st->slots[ticket % st->depth];
+  if (s.ticket != ticket)
+    return fail(GST_ERR_INVALID, "frame %llu is not in flight (its slot holds frame %llu)", (unsigned long long)ticket,
+                (unsigned long long)s.ticket);
+  DeviceGuard guard(st->ctx->device);
+  GST_CUDA_TRY(cudaEventSynchronize(s.done));
+  if (frame_dev) *frame_dev = s.frame_dev;
+  return GST_OK;
 }
 
 // ---- standalone rANS decoder -----------------------------------------------------------

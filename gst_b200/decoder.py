@@ -397,6 +397,49 @@ class Decoder:
         return ((t >> 11) & 0xFF).astype(np.uint8), freq.astype(np.uint16), (slot - bias).astype(np.uint16)
 
 
+class FrameStreamer:
+    """gst_streamer_*: the headless demo player (demo/demo.cpp:145-243) with `depth` frames in flight."""
+
+    def __init__(self, dec, width, height, depth=4, mode=0):
+        self.dec, self.frame_bytes = dec, (width * height * 3 if mode else width * height // 2)
+        h = C.c_void_p()
+        check(lib().gst_streamer_create(dec.ctx, width, height, depth, int(mode), C.byref(h)))
+        self.handle = h
+
+    def submit(self, frame, out=None):
+        """frame: .gst bytes (numpy array or PinnedBuffer); out: optional DeviceBuffer.  Returns the ticket."""
+        ptr, n = (frame.ptr, frame.nbytes) if isinstance(frame, PinnedBuffer) else (_as_u8(frame).ctypes.data, _as_u8(frame).size)
+        t = C.c_uint64()
+        check(lib().gst_streamer_submit(self.handle, ptr, n, out.ptr if out is not None else None, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        """Blocks until the frame is decoded; returns its device address."""
+        p = C.c_void_p()
+        check(lib().gst_streamer_wait(self.handle, ticket, C.byref(p)))
+        return p.value
+
+    def read(self, ticket):
+        """wait() + download of the frame (test helper)."""
+        ptr = self.wait(ticket)
+        out = np.empty(self.frame_bytes, dtype=np.uint8)
+        s = self.dec.GetDefaultCommandQueue()
+        check(lib().gst_download_async(self.dec.ctx, s, out.ctypes.data, ptr, out.size))
+        self.dec.sync(s)
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().gst_streamer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class AnsDecoder:
     """ans::ocl::OpenCLDecoder (ans/ans_ocl.h:26-72)."""
 

@@ -143,6 +143,22 @@ int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, con
 int gst_load_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens,
                         uint32_t n, uint32_t page, int mode, void *out_dev, size_t out_cap);
 
+/* ---- frame streamer: the headless form of the demo player (demo/demo.cpp:145-243,504-600), which
+ * reads frameNNNN.gtc, uploads it, calls LoadCompressedDXT / LoadRGB and blocks on the event
+ * before the next frame.  Here `depth` frames are in flight: submit() packs the frame into the
+ * slot's pinned staging, copies it to the device and decodes it on the slot's own stream; it only
+ * blocks when the slot's previous frame (ticket - depth) is still running.  mode 0 = DXT1, 1 = RGB8
+ * (LoadRGB, demo/demo.cpp:208-212).  out_dev NULL decodes into the slot's own device frame.
+ * wait() blocks until that frame is complete and returns where it was decoded to; a frame stays
+ * valid until `depth` further frames have been submitted. */
+typedef struct gst_streamer gst_streamer;
+int gst_streamer_create(gst_ctx *ctx, uint32_t width, uint32_t height, uint32_t depth, int mode,
+                        gst_streamer **out);
+int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev,
+                        uint64_t *ticket);
+int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev);
+void gst_streamer_destroy(gst_streamer *st);
+
 /* ---- stage taps for the parity tests (not used in production).  Any pointer may be NULL.
  *   symbols_dev : sum(7N + P) bytes, reference decmp_buf layout (codec/decoder.cpp:212)
  *   planes_dev  : n*6N int8, raster planes (codec/decoder.cpp:280)

@@ -230,3 +230,31 @@ def test_load_host_batch_resident(decoder, pinned):
     for pos, j in enumerate(order):
         assert np.array_equal(got[pos * per:(pos + 1) * per], srcs[j][1]), f"image {pos}"
     d_out.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_frame_streamer(decoder, mode):
+    """gst_streamer_*: the demo player loop (demo/demo.cpp:145-243) with 3 frames in flight, DXT1
+    and RGB8 (LoadRGB) outputs; every frame checked, including after the slots wrapped around."""
+    import gst_b200
+    srcs = [fx.encode_image(1920, 1024, 40000 + i) for i in range(3)]
+    want = [fx.oracle_decode(g, mode=mode, taps=False)["out"] for g, _ in srcs]
+    st = gst_b200.FrameStreamer(decoder, 1920, 1024, depth=3, mode=mode)
+    try:
+        tickets = []
+        for f in range(10):
+            tickets.append(st.submit(srcs[f % 3][0]))
+            if f >= 2:  # consume two frames behind the producer
+                k = f - 2
+                got = st.read(tickets[k])
+                assert np.array_equal(got, want[k % 3]), f"frame {k}"
+        for k in (8, 9):
+            assert np.array_equal(st.read(tickets[k]), want[k % 3]), f"frame {k}"
+        with pytest.raises(gst_b200.GstError):
+            st.wait(tickets[0])  # long gone: its slot holds a later frame
+        with pytest.raises(gst_b200.GstError):
+            st.submit(srcs[0][0][:100])  # truncated frame
+        with pytest.raises(gst_b200.GstError):
+            st.submit(fx.golden_test1()[0])  # 512x512 into a 1920x1024 streamer
+    finally:
+        st.close()
