@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--images", type=int, default=0, help="override images per GPU")
     ap.add_argument("--distinct", type=int, default=32, help="distinct encoded images tiled to the batch")
     ap.add_argument("--page", type=int, default=32, help="images per page on the e2e path")
+    ap.add_argument("--depth", type=int, default=4, help="frames in flight of the configs[4] frame streamer")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="weak: every GPU decodes the whole configured batch; strong: the batch is sharded, "
@@ -309,8 +310,23 @@ def main():
         ptrs = (C.c_void_p * images)(*[pin_files[j].ptr for j in order])
         lens = (C.c_size_t * images)(*[files[j].size for j in order])
 
+        streamer = gst_b200.FrameStreamer(dec, width, height, depth=args.depth) if args.config == 4 else None
+
         def e2e_step():
-            check(lib().gst_decompress_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, pin_out.ptr, pin_out.nbytes))
+            if streamer is None:
+                check(lib().gst_decompress_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, pin_out.ptr, pin_out.nbytes))
+                return
+            # configs[4]: the demo player loop (demo/demo.cpp:145-243) with `depth` frames in flight; every
+            # frame is copied back to the host as soon as it is decoded
+            tickets = []
+            for f in range(images):
+                tickets.append(streamer.submit(pin_files[order[f]]))
+                if f >= args.depth - 1:
+                    k = f - (args.depth - 1)
+                    check(lib().gst_download_async(dec.ctx, stream, pin_out.ptr + k * 8 * N, streamer.wait(tickets[k]), 8 * N))
+            for k in range(max(0, images - (args.depth - 1)), images):
+                check(lib().gst_download_async(dec.ctx, stream, pin_out.ptr + k * 8 * N, streamer.wait(tickets[k]), 8 * N))
+            dec.sync(stream)
 
         e2e_step()  # warm-up: grows the staging buffers
         assert fx.matches_golden(pin_out.array[: 8 * N], goldens[order[0]]), "e2e output differs"
@@ -327,7 +343,10 @@ def main():
                "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(d2h_job),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
+               "api": "gst_streamer_submit/wait per frame" if streamer is not None else "gst_decompress_host_batch",
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
+        if streamer is not None:
+            streamer.close()
     # ---- photos_sf shape: host .gst buffers -> textures resident in device memory ---------------
     e2e_res = None
     if not args.no_e2e:

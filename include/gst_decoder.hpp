@@ -199,6 +199,50 @@ inline gst_mem UploadData(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, const
   return m;
 }
 
+// The page loop of demo/photos_sf.cpp:688-885 as one call: host .gst files -> textures in a
+// caller-owned device buffer (image i at i * W*H/2), pages of `page` images over the work queues.
+inline void LoadHostBatch(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, const std::vector<std::vector<uint8_t> > &files,
+                          gst_mem output, uint32_t page = 16) {
+  std::vector<const uint8_t *> ptrs;
+  std::vector<size_t> lens;
+  for (const auto &f : files) {
+    ptrs.push_back(f.data());
+    lens.push_back(f.size());
+  }
+  if (gst_load_host_batch(gpu_ctx->Handle(), ptrs.data(), lens.data(), static_cast<uint32_t>(files.size()), page, 0,
+                          output.ptr, output.bytes) != GST_OK)
+    throw std::runtime_error(gst_last_error());
+}
+
+// The frame loop of demo/demo.cpp:145-243 (read frameNNNN.gtc, upload, LoadCompressedDXT or LoadRGB,
+// wait) with `depth` frames in flight instead of one.
+class FrameStreamer {
+ public:
+  FrameStreamer(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, uint32_t width, uint32_t height, uint32_t depth = 4,
+                bool rgb = false) {
+    if (gst_streamer_create(gpu_ctx->Handle(), width, height, depth, rgb ? 1 : 0, &_st) != GST_OK)
+      throw std::runtime_error(gst_last_error());
+  }
+  ~FrameStreamer() { gst_streamer_destroy(_st); }
+  FrameStreamer(const FrameStreamer &) = delete;
+  FrameStreamer &operator=(const FrameStreamer &) = delete;
+  // returns the ticket of the frame; blocks only when `depth` frames are already in flight
+  uint64_t Submit(const std::vector<uint8_t> &frame, void *out_dev = nullptr) {
+    uint64_t t = 0;
+    if (gst_streamer_submit(_st, frame.data(), frame.size(), out_dev, &t) != GST_OK) throw std::runtime_error(gst_last_error());
+    return t;
+  }
+  // blocks until the frame is decoded; device address of its DXT1 blocks / RGB texels
+  void *Wait(uint64_t ticket) {
+    void *p = nullptr;
+    if (gst_streamer_wait(_st, ticket, &p) != GST_OK) throw std::runtime_error(gst_last_error());
+    return p;
+  }
+
+ private:
+  gst_streamer *_st = nullptr;
+};
+
 }  // namespace GenTC
 
 namespace ans {

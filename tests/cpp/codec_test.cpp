@@ -85,6 +85,31 @@ int main(int argc, char **argv) {
   }
   GenTC::FreeDecompressor(ctx);
 
+  // the photos_sf page loop as one call (host files -> device textures), ragged last page
+  {
+    std::vector<std::vector<uint8_t> > batch_files(5, cmp_data);
+    gst_mem textures = ctx->CreateBuffer(5 * golden.size());
+    GenTC::LoadHostBatch(ctx, batch_files, textures, 2);
+    for (int i = 0; i < 5; ++i) {
+      ctx->ReadBuffer(q, textures, i * golden.size(), host.data(), host.size(), true);
+      EXPECT(host == golden);
+    }
+  }
+
+  // the demo frame loop with 2 frames in flight
+  {
+    GenTC::FrameStreamer player(ctx, 512, 512, 2);
+    uint64_t t0 = player.Submit(cmp_data), t1 = player.Submit(cmp_data);
+    for (uint64_t t : {t0, t1}) {
+      void *frame = player.Wait(t);
+      gst_mem view;
+      view.ptr = frame;
+      view.bytes = golden.size();
+      ctx->ReadBuffer(q, view, 0, host.data(), host.size(), true);
+      EXPECT(host == golden);
+    }
+  }
+
   // ans::ocl table interface (ans/ans_ocl_test.cpp:64-108)
   std::vector<uint32_t> F = {3, 2, 1, 4, 3};
   ans::ocl::OpenCLDecoder decoder(ctx, F, 1);
