@@ -258,3 +258,58 @@ def test_frame_streamer(decoder, mode):
             st.submit(fx.golden_test1()[0])  # 512x512 into a 1920x1024 streamer
     finally:
         st.close()
+
+
+def _sweeping_gst(width, height, palette_entries, seed):
+    """Like fx.random_gst, but the palette index sweeps the whole palette (a triangle wave with steps
+    of up to 127), so indices above 2^16 really occur."""
+    rng = np.random.default_rng(seed)
+    n = (width // 4) * (height // 4)
+    planes = np.clip(np.rint(rng.laplace(0.0, 6.0, size=6 * n)) + 128, 0, 255).astype(np.uint8)
+    pal_bytes = -(-palette_entries * 4 // fx.GROUP) * fx.GROUP
+    palette = np.zeros(pal_bytes, dtype=np.uint8)
+    palette[: palette_entries * 4] = rng.integers(0, 256, size=palette_entries * 4, dtype=np.uint8)
+    idx = np.empty(n, dtype=np.int64)
+    cur, direction = 0, 1
+    steps = rng.integers(90, 128, size=n)
+    for i in range(n):
+        nxt = cur + direction * int(steps[i])
+        if nxt < 0 or nxt >= palette_entries:
+            direction = -direction
+            nxt = cur + direction * int(steps[i])
+        idx[i] = cur = nxt
+    deltas = np.diff(np.concatenate([[0], idx])) + 128
+    assert deltas.min() >= 0 and deltas.max() <= 255 and idx.max() > 66000
+    return fx.make_gst(width, height, planes[: 2 * n], planes[2 * n:], palette, deltas.astype(np.uint8))
+
+
+def test_wide_palette_uses_32_bit_index_sums(decoder):
+    """More than 65536 palette entries: the per-block index suffix sums no longer fit 16 bits and the
+    u32 form of S is used (the reference's decoded_indices are int32, codec/decoder.cpp:302).  Two
+    images in one call, one of them with a small palette, so the batch-wide choice is exercised."""
+    big = _sweeping_gst(1024, 1024, 70000, seed=77)   # N = 65536 blocks, indices up to ~70000
+    small = fx.random_gst(1024, 1024, seed=78, palette_entries=900)
+    res = decoder.decode_tapped([small, big])
+    _check_stages(res, 0, small)
+    _check_stages(res, 1, big)
+    assert int(res["indices"][65536:].max()) > 66000
+
+
+def test_malformed_streams_do_not_fault(decoder):
+    """The reference has no bounds checks in its kernels (a malformed stream is
+    undefined behaviour).  Here garbage payloads, garbage group offsets and garbage frequency
+    tables must come back as ordinary (meaningless) output without a CUDA fault, and the context
+    must still decode a good stream afterwards."""
+    good, golden = fx.golden_test1()
+    rng = np.random.default_rng(5)
+    bad = []
+    a = good.copy(); a[28 + 2048:] = rng.integers(0, 256, size=a.size - 28 - 2048, dtype=np.uint8); bad.append(a)   # payload + offsets
+    b = good.copy(); b[28:28 + 2048] = rng.integers(0, 256, size=2048, dtype=np.uint8); bad.append(b)              # frequency tables
+    c = good.copy(); c[28 + 2048:28 + 2048 + 64] = 0xFF; bad.append(c)                                            # huge group offsets
+    d = good.copy(); d[28 + 2048:28 + 2048 + 64] = 0x00; bad.append(d)                                            # zero group offsets
+    for k, f in enumerate(bad):
+        out = decoder.DecompressDXT(f)
+        assert out.size == golden.size, f"case {k}"
+    out = decoder.DecompressDXTs(bad + [good], page=5)
+    assert np.array_equal(out[4 * golden.size:], golden), "a good image next to malformed ones must still decode"
+    assert np.array_equal(decoder.DecompressDXT(good), golden)
