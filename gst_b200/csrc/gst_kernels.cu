@@ -205,7 +205,9 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
     for (int c = 0; c < NC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      // checkpoint: top up when < kRing - kChunk bytes are staged, then let the two newest groups fly
+      // checkpoint: top up when < kRing - kChunk bytes are staged, then let the two newest groups fly.
+      // The chunk that is topped up replaces words other lanes read during the last 8 symbols.
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (cur2[c] + 2u - static_cast<uint32_t>(lo[c]) < static_cast<uint32_t>(kRing - kChunk)) {
