@@ -72,9 +72,6 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-}
 __device__ __forceinline__ uint32_t lanemask_gt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
@@ -255,10 +252,6 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
     for (int c = 0; c < NC; ++c) emit(c, m, acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
   }
   cp_async_wait_group<0>();
-}
-
-__device__ __forceinline__ void trap_unless_aligned(uint32_t s, uint32_t align) {
-  if (s & (align - 1)) __trap();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -662,7 +655,7 @@ constexpr int kWaSmem = kWaWarps * kWarpWork;  // 36864
 
 template <int RGB>
 __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(const BatchParams p) {
-  extern __shared__ __align__(2048) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
   const uint32_t wl_s = w_s + kWBytes;
