@@ -166,7 +166,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
   const uintptr_t lo16 = (reinterpret_cast<uintptr_t>(buf_lo) + 15) & ~static_cast<uintptr_t>(15);
   const uintptr_t hi16 = reinterpret_cast<uintptr_t>(buf_hi) & ~static_cast<uintptr_t>(15);
 
-  uint32_t state[NC], cur2[NC];
+  uint32_t state[NC], pos[NC], mprev[NC];
   uintptr_t lo[NC];
   uint32_t end[NC];
 #pragma unroll
@@ -189,12 +189,20 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
       if (a >= lo16 && a + 16 <= hi16)
         cp_async16(ring_s + c * kRing + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
     }
-    cur2[c] = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
+    pos[c] = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
+    mprev[c] = 0u;
   }
   cp_async_commit();
   cp_async_wait_group<0>();
   __syncwarp();
 
+  // Word addressing with ONE popcount per symbol.  The reference gives lane l the word at
+  //   next - 1 - popc(mask_t & lanes_above_l),  next -= popc(mask_t)     (ans/ans_decode.cl:51-65).
+  // Here every lane keeps its own address pos_l(t) = next(t) - popc(mask_t & gt_l) (in bytes): then
+  //   pos_l(t+1) = pos_l(t) - popc(mask_t & ~gt_l) - popc(mask_{t+1} & gt_l)
+  //              = pos_l(t) - popc((mask_t & ~gt_l) | (mask_{t+1} & gt_l))     (disjoint bit ranges)
+  // which is one LOP3 + one POPC instead of two of each.  At a checkpoint the uniform `next` is
+  // recovered as pos_l - popc(mask & ~gt_l) and the recurrence restarts with mask = 0.
 #pragma unroll 1
   for (int m = 0; m < 16; ++m) {
     uint32_t acc[NC][4];
@@ -207,7 +215,9 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        if (cur2[c] + 2u - static_cast<uint32_t>(lo[c]) < static_cast<uint32_t>(kRing - kChunk)) {
+        pos[c] -= 2u * __popc(mprev[c] & ~gt);  // uniform again: address of the next unread word
+        mprev[c] = 0u;
+        if (pos[c] + 2u - static_cast<uint32_t>(lo[c]) < static_cast<uint32_t>(kRing - kChunk)) {
           lo[c] -= kChunk;
           const uintptr_t a = lo[c] + 16 * lane;
           if (a >= lo16 && a + 16 <= hi16)
@@ -221,29 +231,32 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
       for (int k = 0; k < 8; ++k) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          uint32_t slot_a;  // tab_s + 4 * (state & 2047)
-          asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(state[c] & (kTableSize - 1)), "r"(tab_s));
+          const uint32_t slot = state[c] & (kTableSize - 1);
+          uint32_t slot_a;  // tab_s + 4 * slot
+          asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(slot), "r"(tab_s));
           const uint32_t e = lds32(slot_a);
-          // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  Written as multiplies so
-          // that those shifts issue on the FMA pipe; the bias shift stays on the ALU pipe, which balances
-          // the two (measured: all three on the FMA pipe is 3 % slower, all on the ALU pipe 10 %).
-          uint32_t f21, sym24, hi;
-          int32_t bias;
+          // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  The shifts of freq and symbol
+          // are written as multiplies so that they issue on the FMA pipe.  The multiply-high is left to
+          // the compiler as a 64-bit product: it then folds the bias shift and the add into one
+          // LEA.HI.SX32 (hi + (e >> 19)), where the mul.hi/add form makes ptxas put the bias in the
+          // 64-bit addend of IMAD.HI and re-zero the low half of that register pair every step.
+          uint32_t f21, sym24;
           asm("mul.lo.u32 %0, %1, 2097152;" : "=r"(f21) : "r"(e));   // e << 21
-          bias = static_cast<int32_t>(e) >> 19;                      // SHF on the ALU pipe: two IMAD.HI per step would load the FMA pipe more than the ALU pipe
           asm("mul.lo.u32 %0, %1, 8192;" : "=r"(sym24) : "r"(e));    // e << 13: symbol in the top byte
-          asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(state[c]), "r"(f21));
-          state[c] = hi + static_cast<uint32_t>(bias);
+          state[c] = static_cast<uint32_t>((static_cast<uint64_t>(state[c]) * f21) >> 32) +
+                     static_cast<uint32_t>(static_cast<int32_t>(e) >> 19);
           const bool need = FULL ? (state[c] < kRansL) : (active && state[c] < kRansL);
           const uint32_t mask = __ballot_sync(0xffffffffu, need);
-          const uint32_t a = cur2[c] - 2u * __popc(mask & gt);
-          uint32_t ra;  // (a & (kRing - 1)) | ring in one LOP3 (the ring is kRing-aligned)
-          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(a), "n"(kRing - 1), "r"(ring_s + c * kRing));
+          uint32_t sel;  // (mask & gt) | (mprev & ~gt)
+          asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(sel) : "r"(mask), "r"(mprev[c]), "r"(gt));
+          pos[c] -= 2u * __popc(sel);
+          mprev[c] = mask;
+          uint32_t ra;  // (pos & (kRing - 1)) | ring in one LOP3 (the ring is kRing-aligned)
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(pos[c]), "n"(kRing - 1), "r"(ring_s + c * kRing));
           const uint32_t w = lds_u16(ra);
           uint32_t renorm;  // state << 16 | w
           asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state[c]), "r"(w));
           if (need) state[c] = renorm;
-          cur2[c] -= 2u * __popc(mask);                                 // ans/ans_decode.cl:65
           const int word = 3 - 2 * h - (k >> 2);
           acc[c][word] = __byte_perm(acc[c][word], sym24, 0x2107);      // acc << 8 | symbol
         }
