@@ -16,7 +16,7 @@ SOURCES = ["gst_kernels.cu", "gst_capi.cu"]
 DEPS = SOURCES + ["gst_kernels.cuh", os.path.join("..", "..", "include", "gst_cuda.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared", "-x", "cu",
+    "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared", "-x", "cu",] + os.environ.get("GST_NVCC_EXTRA", "").split() + [
 ]
 
 

@@ -39,11 +39,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
   asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
   return v;
 }
-__device__ __forceinline__ int lds_s16(uint32_t a) {
-  int v;
-  asm volatile("{ .reg .s16 t; ld.shared.s16 t, [%1]; cvt.s32.s16 %0, t; }" : "=r"(v) : "r"(a));
-  return v;
-}
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -53,12 +48,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
-}
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
-  asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u8 [%0], t; }" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
-  asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -101,19 +90,6 @@ template <int J>
 __device__ __forceinline__ uint32_t sext_byte_pair(uint32_t w) {
   return prmt<((8 | (J + 1)) << 12) | ((J + 1) << 8) | ((8 | J) << 4) | J>(w, 0u);
 }
-__device__ __forceinline__ int lo16(uint32_t w) {
-  int d;
-  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x0001u), "r"(0));
-  return d;
-}
-__device__ __forceinline__ int hi16(uint32_t w) {
-  int d;
-  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x0100u), "r"(0));
-  return d;
-}
-__device__ __forceinline__ uint32_t pack16(int a, int b) {
-  return __byte_perm(static_cast<uint32_t>(a), static_cast<uint32_t>(b), 0x5410);
-}
 
 // ---------------------------------------------------------------------------------------
 // Stage 2 core: one warp decodes one group of `n_lanes` interleaved rANS streams.
@@ -146,18 +122,23 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// NC = 1 or 2 groups per warp.  With NC = 2 the warp decodes groups `group` and `group + 1` of the
-// same stream in one interleaved instruction stream: the decode step is a chain of ~14 dependent
+// NC = 1 or 2 groups per warp.  With NC = 2 the warp decodes groups grp[0] and grp[1] of the
+// same stream in one interleaved instruction stream: the decode step is a chain of ~12 dependent
 // instructions (two of them shared-memory loads), and two independent chains per warp hide
 // that latency better than twice the warps would (registers, not warps, are what is left).
 // Chain c uses the ring at ring_s + c * kRing.
-// emit(c, m, w0, w1, w2, w3): called 16 times per chain; the 16 symbols at positions
-// q0 = 240 - 16m .. q0 + 15 of this lane's 256-symbol run of chain c, little-endian packed
-// (w0 = q0..q0+3, ..., w3 = q0+12..q0+15).
-template <bool FULL, int NC, class Emit>
+// emit(m, acc): called 16 times; acc holds the 16 symbols at positions q0 = 240 - 16m .. q0 + 15 of
+// this lane's 256-symbol run of every chain:
+//   ILV = false: acc[4c + j] = symbols q0 + 4j .. q0 + 4j + 3 of chain c, little-endian packed
+//   ILV = true (NC = 2): the two chains byte-interleaved, acc[j] = {chain 0 @ q0 + 2j, chain 1 @ q0 + 2j,
+//                chain 0 @ q0 + 2j + 1, chain 1 @ q0 + 2j + 1} -- the layout wavelet_assemble_kernel
+//                unpacks with one PRMT per coefficient pair; it costs nothing here because the
+//                PRMT that files a symbol away takes any destination byte.
+template <bool FULL, int NC, bool ILV, class Emit>
 __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t *__restrict__ stream,
-                                                   uint32_t group, uint32_t n_lanes, uint32_t ring_s,
+                                                   const uint32_t (&grp)[NC], uint32_t n_lanes, uint32_t ring_s,
                                                    const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
+  static_assert(!ILV || NC == 2, "interleaved output needs two chains");
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gt = lanemask_gt();
   const bool active = FULL || lane < n_lanes;
@@ -170,7 +151,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
   uintptr_t lo[NC];
   uint32_t end[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) end[c] = __ldg(reinterpret_cast<const uint32_t *>(stream) + group + c) & ~3u;  // ans/ans_decode.cl:30
+  for (int c = 0; c < NC; ++c) end[c] = __ldg(reinterpret_cast<const uint32_t *>(stream) + grp[c]) & ~3u;  // ans/ans_decode.cl:30
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     // Clamp so a malformed offset can never leave [buf_lo, buf_hi).
@@ -205,9 +186,9 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
   // recovered as pos_l - popc(mask & ~gt_l) and the recurrence restarts with mask = 0.
 #pragma unroll 1
   for (int m = 0; m < 16; ++m) {
-    uint32_t acc[NC][4];
+    uint32_t acc[NC * 4];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0u;
+    for (int j = 0; j < NC * 4; ++j) acc[j] = 0u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       // checkpoint: top up when < kRing - kChunk bytes are staged, then let the two newest groups fly.
@@ -257,13 +238,20 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
           uint32_t renorm;  // state << 16 | w
           asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state[c]), "r"(w));
           if (need) state[c] = renorm;
-          const int word = 3 - 2 * h - (k >> 2);
-          acc[c][word] = __byte_perm(acc[c][word], sym24, 0x2107);      // acc << 8 | symbol
+          const int q = 15 - 8 * h - k;  // position inside this 16-symbol piece (symbols arrive last first)
+          if (ILV) {
+            // byte 2 (q & 1) + c of word q / 2 <- symbol
+            constexpr uint32_t kIns[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};
+            const int byte = 2 * (q & 1) + c;
+            acc[q >> 1] = byte == 0 ? __byte_perm(acc[q >> 1], sym24, kIns[0]) : byte == 1 ? __byte_perm(acc[q >> 1], sym24, kIns[1])
+                        : byte == 2 ? __byte_perm(acc[q >> 1], sym24, kIns[2]) : __byte_perm(acc[q >> 1], sym24, kIns[3]);
+          } else {
+            acc[4 * c + (q >> 2)] = __byte_perm(acc[4 * c + (q >> 2)], sym24, 0x2107);  // acc << 8 | symbol
+          }
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) emit(c, m, acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+    emit(m, acc);
   }
   cp_async_wait_group<0>();
 }
@@ -398,33 +386,60 @@ struct StreamGrid {
   __host__ __device__ uint32_t per_image() const { return y_ctas + c_ctas + pal_ctas + idx_ctas; }
 };
 
-// One warp's share of a stream: NC consecutive groups starting at `group`.
-template <int NC>
+// One warp's share of the Y or chroma stream: one group of plane A and the same group of plane B
+// of a plane pair -- pair 0 = (Y1, Y2), pair 1 = (Co1, Co2), pair 2 = (Cg1, Cg2), i.e. the two
+// endpoints' planes of one colour channel, which the wavelet and the assembly process as the two
+// 16-bit halves of one register.  Stream order (codec/encoder.cpp:87,93-95): Y = Y1 || Y2,
+// chroma = Co1 || Cg1 || Co2 || Cg2, every plane groups_per_plane groups long.
+template <bool TAP>
+__device__ __forceinline__ void rans_plane_pair(const BatchParams &p, uint32_t b, uint32_t pair, uint32_t g,
+                                                const uint8_t *stream, uint32_t out_off, uint32_t tab_s, uint32_t ring_s) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gpp = p.groups_per_plane;
+  const uint32_t grp[2] = {pair == 2 ? gpp + g : g, pair == 0 ? gpp + g : pair == 1 ? 2 * gpp + g : 3 * gpp + g};
+  uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + lane * kSymsPerLane + 240 : nullptr;
+  uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + (static_cast<size_t>(pair) * gpp + g) * (2 * kGroupSyms) +
+                 15 * 1024 + lane * 32;
+  rans_decode_groups<true, 2, true>(tab_s, stream, grp, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                                    [&](int m, const uint32_t (&w)[8]) {
+                                      *reinterpret_cast<uint4 *>(dst - 1024 * m) = make_uint4(w[0], w[1], w[2], w[3]);
+                                      *reinterpret_cast<uint4 *>(dst - 1024 * m + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                                      if (TAP && tap) {
+#pragma unroll
+                                        for (int c = 0; c < 2; ++c) {
+                                          const uint32_t sel = c ? 0x7531u : 0x6420u;
+                                          *reinterpret_cast<uint4 *>(tap + static_cast<size_t>(grp[c]) * kGroupSyms - 16 * m) =
+                                              make_uint4(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel),
+                                                         __byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel));
+                                        }
+                                      }
+                                    });
+}
+
+// One warp's share of the palette or index stream: NC consecutive groups starting at `group`.
+template <int NC, bool TAP>
 __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_t b, uint32_t type, uint32_t group,
                                                    const uint8_t *stream, uint32_t out_off, uint32_t pal_off,
                                                    uint32_t tab_s, uint32_t ring_s) {
   const uint32_t lane = threadIdx.x & 31;
-  uint8_t *tap = p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 240
-                               : nullptr;
-  if (type < 2) {
-    const size_t pg = (type ? 2 * p.groups_per_plane : 0) + group;
-    uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + pg * kGroupSyms + 15 * 512 + lane * 16;
-    rans_decode_groups<true, NC>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                                 [&](int c, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                                   *reinterpret_cast<uint4 *>(dst + c * kGroupSyms - 512 * m) = make_uint4(w0, w1, w2, w3);
-                                   if (tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
-                                 });
-    return;
-  }
+  uint32_t grp[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) grp[c] = group + c;
+  uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 240
+                                      : nullptr;
   if (type == 2) {
     const uint64_t off = static_cast<uint64_t>(pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
     const bool ok = off + NC * kGroupSyms <= p.palette_cap;
     uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
-    rans_decode_groups<true, NC>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                                 [&](int c, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                                   if (ok) *reinterpret_cast<uint4 *>(dst + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
-                                   if (tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
-                                 });
+    rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                                        [&](int m, const uint32_t (&w)[NC * 4]) {
+#pragma unroll
+                                          for (int c = 0; c < NC; ++c) {
+                                            const uint4 v = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                                            if (ok) *reinterpret_cast<uint4 *>(dst + c * kGroupSyms - 16 * m) = v;
+                                            if (TAP && tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = v;
+                                          }
+                                        });
     return;
   }
 
@@ -435,28 +450,31 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
   const bool idx16 = p.idx16 != 0;
-  rans_decode_groups<true, NC>(tab_s, stream, group, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
-                               [&](int c, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                                 if (tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w0, w1, w2, w3);
-                                 const uint32_t w[4] = {w0, w1, w2, w3};
-                                 uint32_t s[16];
+  rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+                               [&](int m, const uint32_t (&wa)[NC * 4]) {
 #pragma unroll
-                                 for (int i = 15; i >= 0; --i) {
-                                   s[i] = sum[c];
-                                   sum[c] += ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 128u;
-                                 }
-                                 if (idx16) {
-                                   uint32_t q[8];
+                                 for (int c = 0; c < NC; ++c) {
+                                   const uint32_t w[4] = {wa[4 * c], wa[4 * c + 1], wa[4 * c + 2], wa[4 * c + 3]};
+                                   if (TAP && tap) *reinterpret_cast<uint4 *>(tap + c * kGroupSyms - 16 * m) = make_uint4(w[0], w[1], w[2], w[3]);
+                                   uint32_t s[16];
 #pragma unroll
-                                   for (int i = 0; i < 8; ++i) q[i] = __byte_perm(s[2 * i], s[2 * i + 1], 0x5410);
-                                   uint16_t *d = dst16 + c * kGroupSyms - 512 * m;
-                                   *reinterpret_cast<uint4 *>(d) = make_uint4(q[0], q[1], q[2], q[3]);
-                                   *reinterpret_cast<uint4 *>(d + 8) = make_uint4(q[4], q[5], q[6], q[7]);
-                                 } else {
-                                   uint32_t *d = dst32 + c * kGroupSyms - 512 * m;
+                                   for (int i = 15; i >= 0; --i) {
+                                     s[i] = sum[c];
+                                     sum[c] += ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 128u;
+                                   }
+                                   if (idx16) {
+                                     uint32_t q[8];
 #pragma unroll
-                                   for (int i = 0; i < 4; ++i)
-                                     *reinterpret_cast<uint4 *>(d + 4 * i) = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+                                     for (int i = 0; i < 8; ++i) q[i] = __byte_perm(s[2 * i], s[2 * i + 1], 0x5410);
+                                     uint16_t *d = dst16 + c * kGroupSyms - 512 * m;
+                                     *reinterpret_cast<uint4 *>(d) = make_uint4(q[0], q[1], q[2], q[3]);
+                                     *reinterpret_cast<uint4 *>(d + 8) = make_uint4(q[4], q[5], q[6], q[7]);
+                                   } else {
+                                     uint32_t *d = dst32 + c * kGroupSyms - 512 * m;
+#pragma unroll
+                                     for (int i = 0; i < 4; ++i)
+                                       *reinterpret_cast<uint4 *>(d + 4 * i) = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+                                   }
                                  }
                                });
   // group-local inclusive prefix at the end of every run, and the group total
@@ -473,6 +491,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   }
 }
 
+template <bool TAP>
 __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // the rings are indexed by OR-ing low address bits, so they must be kRing-aligned; the dynamic
@@ -491,23 +510,33 @@ __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const 
   else if ((r -= sg.c_ctas) < sg.pal_ctas) type = 2;
   else { r -= sg.pal_ctas; type = 3; }
   const ImageStreams is = image_streams(p, b);
-  const uint32_t n_groups = type == 0 ? 2 * p.groups_per_plane : type == 1 ? 4 * p.groups_per_plane
-                          : type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
-  const uint32_t first = r * kRansGroupsPerCta;
-  if (first >= n_groups) return;
-
-  load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
-  __syncthreads();
-  const uint32_t group = first + warp * kRansChains;
-  if (group >= n_groups) return;
   // in_off[type] / out_off[type] by selection (a dynamically indexed array would live in local memory)
   const uint32_t in_off = type == 0 ? is.in_off[0] : type == 1 ? is.in_off[1] : type == 2 ? is.in_off[2] : is.in_off[3];
   const uint32_t out_off = type == 0 ? is.out_off[0] : type == 1 ? is.out_off[1] : type == 2 ? is.out_off[2] : is.out_off[3];
   const uint8_t *stream = is.payload + in_off;
+  if (type < 2) {
+    // work items of a plane stream: (pair, group); Y has groups_per_plane of them, chroma twice as many
+    const uint32_t n_items = (type + 1) * p.groups_per_plane;
+    if (r * kRansWarps >= n_items) return;
+    load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
+    __syncthreads();
+    const uint32_t item = r * kRansWarps + warp;
+    if (item >= n_items) return;
+    const uint32_t pair = type == 0 ? 0u : 1u + item / p.groups_per_plane;
+    rans_plane_pair<TAP>(p, b, pair, item % p.groups_per_plane, stream, out_off, tab_s, ring_s);
+    return;
+  }
+  const uint32_t n_groups = type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
+  const uint32_t first = r * kRansGroupsPerCta;
+  if (first >= n_groups) return;
+  load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
+  __syncthreads();
+  const uint32_t group = first + warp * kRansChains;
+  if (group >= n_groups) return;
   if (group + 1 < n_groups)
-    rans_stream_groups<2>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
+    rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
   else
-    rans_stream_groups<1>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
+    rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
 }
 
 // The cross-group part of stage 3 (what the collect_indices passes of
@@ -546,134 +575,263 @@ __global__ void __launch_bounds__(256) index_carry_kernel(const BatchParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Stage 4 helpers.  1-D inverse 5/3 lifting of v = [low half | high half] in registers,
-// codec/inverse_wavelet.cl:28-64 (NormalizeIndex mirror resolved at compile time):
-//   even: d[2x]   = s[x]       - (s[mid + max(x-1,0)] + s[mid + x] + 2) / 4
-//   odd : d[2x+1] = s[mid + x] + (d[2x] + d[min(2x+2, len-2)]) / 2          ('/' truncates)
-template <int LEN>
-__device__ __forceinline__ void inverse_lift(int (&v)[LEN]) {
+// Stages 4 + 5 on PACKED PLANE PAIRS.
+//
+// The two endpoints of a DXT1 block go through identical arithmetic: Y1/Y2, Co1/Co2 and Cg1/Cg2 are
+// inverse-transformed by the same lifting steps and then converted by the same YCoCg -> 565
+// formula, and the block's first word is ep1 | ep2 << 16.  So one 32-bit register carries the
+// value of plane A in its low half and of plane B in its high half through the whole kernel,
+// and every add works on both (rans_streams_kernel already delivers the coefficients of a pair
+// byte-interleaved, so unpacking is one PRMT per pair).
+//
+// Representation: each half holds x + bias, with bias = kBias = 4096 for every computed value and
+// kRaw = 0x1080 = 4224 for a freshly unpacked coefficient (byte | 0x10 << 8 = (byte - 128) + 4224).
+// Every wavelet intermediate is bounded by |x| <= 3488 for ANY input bytes (128 + 672 per level), so
+// halves stay in [608, 7712]: non-negative, and sums of three never reach 2^16 -- plain 32-bit adds
+// never carry across the halves.  The reference's truncating divisions
+// (codec/inverse_wavelet.cl:28-64, '/' on ints) are done on T = t + 2^13 (t = the dividend, |t| < 2^13):
+// bit 13 of T is [t >= 0], which gives the round-toward-zero correction without a per-half sign
+// extension, and the bits a 32-bit shift would carry from the high half into the low half are
+// masked off before the shift.
+//
+// Pipes: every LOP3 / SHF / IADD3 / PRMT occupies the ALU pipe for two cycles per warp, and that
+// pipe -- not the issue slots -- bounds this kernel (profiles/: ALU 81 % busy, FMA pipe 15 %, before
+// this was done).  So whatever has a multiplier form is written as one: two-input adds as
+// mad.lo(a, 1, b) (IMAD.IADD), the shifts that produce the quotient as mul.hi by 2^30 / 2^31 (IMAD.HI).
+constexpr int kBias = 4096;
+constexpr int kRaw = 0x1080;
+__host__ __device__ constexpr uint32_t pk(int v) { return static_cast<uint32_t>(v) * 65537u; }  // v in both halves
+constexpr uint32_t kOnes = 0x00010001u;
+
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b) {  // a + b on the FMA pipe
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t fma_sub_from(uint32_t a, uint32_t b) {  // b - a on the FMA pipe
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// x >> (32 - log2 k) as a multiply-high.  ptxas keeps the 2^30 one (the /4 quotient) on the FMA pipe as
+// IMAD.HI and folds the 2^31 one (the /2 quotient) with the add that follows it into one LEA.HI.  Forcing
+// that one onto the FMA pipe as well (multiplier hidden in the kernel parameters) was measured 6 % slower,
+// and so was the sign-bit shift (T >> 13) as a multiply-high (1 %): IMAD.HI is quarter rate and the
+// FMA-heavy pipe becomes the bound.  The /4 quotient as a plain shift, or the adds left to ptxas, are
+// 1-2 % slower the other way (ALU pipe).
+struct ShiftK { uint32_t k30, k31; };
+__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t k) {
+  uint32_t d;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(k));
+  return d;
+}
+
+// d[2x] = s[x] - (h[x-1] + h[x] + 2) / 4.  HB = bias of the h operands; cD = pk(2048 + kBias - bias of S).
+template <int HB>
+__device__ __forceinline__ uint32_t lift_even_p(uint32_t S, uint32_t HP, uint32_t HN, uint32_t cD, const ShiftK &sk) {
+  const uint32_t T = HP + HN + pk(2 + 8192 - 2 * HB);     // t + 2^13
+  const uint32_t neg = ~(T >> 13) & kOnes;                // [t < 0]
+  const uint32_t T3 = neg * 3u + T;                       // trunc(t / 4) = floor((t + 3 [t < 0]) / 4)
+  const uint32_t Q = mulhi(T3 & 0xFFFCFFFCu, sk.k30);     // trunc(t / 4) + 2048
+  return S - Q + cD;
+}
+// d[2x+1] = h[x] + (d[2x] + d[2x+2]) / 2.  The d operands are computed values (bias kBias); cH = pk(-bias of H).
+__device__ __forceinline__ uint32_t lift_odd_p(uint32_t H, uint32_t EP, uint32_t EN, uint32_t cH, const ShiftK &sk) {
+  const uint32_t T = fma_add(EP, EN);                     // t + 2^13
+  const uint32_t neg = ~(T >> 13) & kOnes;                // [t < 0]
+  const uint32_t T2 = fma_add(T, neg);                    // trunc(t / 2) = floor((t + [t < 0]) / 2)
+  const uint32_t X = mulhi(T2 & 0xFFFEFFFEu, sk.k31);     // trunc(t / 2) + 4096
+  return H + X + cH;
+}
+// 1-D inverse 5/3 lifting of v = [low half | high half] in registers, codec/inverse_wavelet.cl:28-64
+// (NormalizeIndex mirror resolved at compile time).  HB = bias of the high half; the result has bias kBias.
+template <int LEN, int HB>
+__device__ __forceinline__ void inverse_lift_p(uint32_t (&v)[LEN], uint32_t cD, const ShiftK &sk) {
   constexpr int MID = LEN / 2;
-  int o[LEN];
+  uint32_t o[LEN];
 #pragma unroll
-  for (int x = 0; x < MID; ++x) {
-    const int hp = v[MID + (x == 0 ? 0 : x - 1)];
-    const int hn = v[MID + x];
-    o[2 * x] = v[x] - (hp + hn + 2) / 4;
-  }
+  for (int x = 0; x < MID; ++x) o[2 * x] = lift_even_p<HB>(v[x], v[MID + (x == 0 ? 0 : x - 1)], v[MID + x], cD, sk);
 #pragma unroll
-  for (int x = 0; x < MID; ++x) {
-    const int ep = o[2 * x];
-    const int en = o[(2 * x + 2 == LEN) ? 2 * x : 2 * x + 2];
-    o[2 * x + 1] = v[MID + x] + (ep + en) / 2;
-  }
+  for (int x = 0; x < MID; ++x)
+    o[2 * x + 1] = lift_odd_p(v[MID + x], o[2 * x], o[(2 * x + 2 == LEN) ? 2 * x : 2 * x + 2], pk(-HB), sk);
 #pragma unroll
   for (int i = 0; i < LEN; ++i) v[i] = o[i];
 }
 
-// Work areas (int16, per warp).  Intermediates are bounded by 128 + 672 per level (<= 3488
-// after five levels) for ANY input bytes, so int16 storage is exact.
-//   Wlow: the 16x16 corners of two planes, 2 x 16 rows of 32 B; the two 16-byte chunks of
-//         row r are swapped when (r >> 2) & 1, which makes lane = row 16-byte accesses and
-//         lane = column 2-byte accesses conflict free without padding.
-//   W   : one 32x32 tile, 32 rows of 64 B, chunk j of row r stored at j ^ ((r >> 1) & 3).
-//   res : the six int8 result planes of the tile, row-major 32x32, read by the assembly.
-constexpr int kWBytes = 2048;
-constexpr int kWlowBytes = 1024;
-constexpr int kResBytes = 6 * kTileSyms;
-constexpr int kWarpWork = kWBytes + kWlowBytes + kResBytes;  // 9216
+// Work area of one warp: three planes W[p] (p = plane pair) of 32 rows x 32 packed words, 128 B per
+// row, the 16-byte chunk j of row r stored at chunk j ^ (r & 7) (lane = row 16-byte accesses, lane =
+// column 4-byte accesses and the assembly's lane = 4 columns accesses are all conflict free).
+// Before a row is transformed at level 32 its logical chunks 4..7 hold the row's 64 raw coefficient
+// bytes (32 columns x {plane A, plane B}), and the top-left 16x16 words of W[p] are the work area of
+// the lower levels: everything is done in place, the tile never leaves these 12 KiB.
+constexpr int kWPlane = 4096;
+constexpr int kWarpWork = 3 * kWPlane;
+__device__ __forceinline__ uint32_t wchunk(uint32_t wp, uint32_t r, uint32_t j) { return wp + r * 128 + (((j ^ r) & 7) << 4); }
 
-// levels 2..16 on two planes at once: lanes 0-15 own plane A, lanes 16-31 plane B.
-// wl = this lane's 512-byte half of Wlow.
+// coefficient pair (col 2m + J of both planes) of an interleaved word {A[2m], B[2m], A[2m+1], B[2m+1]}:
+// byte | 0x10 << 8 in each half = (byte - 128) + kRaw
+template <int J>
+__device__ __forceinline__ uint32_t unp(uint32_t w, uint32_t k10) {
+  return J == 0 ? __byte_perm(w, k10, 0x4140) : __byte_perm(w, k10, 0x4342);
+}
+template <int N>  // N words -> 2N coefficient pairs
+__device__ __forceinline__ void unp_words(const uint32_t (&w)[N], uint32_t *v, uint32_t k10) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) { v[2 * i] = unp<0>(w[i], k10); v[2 * i + 1] = unp<1>(w[i], k10); }
+}
+__device__ __forceinline__ void ld4(uint32_t a, uint32_t *v) { const uint4 t = lds128(a); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+__device__ __forceinline__ void ld2(uint32_t a, uint32_t *v) { const uint2 t = lds64(a); v[0] = t.x; v[1] = t.y; }
+
+// Row r of the level-LEN region: low band = the previous level's result (rows < LEN/2) or raw
+// coefficients, high band = raw coefficients.
 template <int LEN>
-__device__ __forceinline__ void low_level(uint32_t wl, uint32_t lane) {
-  const uint32_t rc = lane & 15;  // row in the row pass, column in the column pass
-  // rows
-  if (rc < LEN) {
-    const uint32_t row = wl + rc * 32 + (((rc >> 2) & 1) << 4);  // logical chunk 0
-    int v[LEN];
-    if (LEN == 16) {
-      const uint4 a = lds128(row), b = lds128(row ^ 16);
-      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+__device__ __forceinline__ void load_row(uint32_t wp, uint32_t r, uint32_t (&v)[LEN], uint32_t k10) {
+  if constexpr (LEN == 32) {
+    uint32_t w[8];
+    if (r < 16) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
-    } else if (LEN == 8) {
-      const uint4 a = lds128(row);
-      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
-    } else if (LEN == 4) {
-      const uint2 a = lds64(row);
-      v[0] = lo16(a.x); v[1] = hi16(a.x); v[2] = lo16(a.y); v[3] = hi16(a.y);
+      for (int j = 0; j < 4; ++j) ld4(wchunk(wp, r, j), v + 4 * j);
     } else {
-      const uint32_t a = lds32(row);
-      v[0] = lo16(a); v[1] = hi16(a);
+      ld4(wchunk(wp, r, 4), w); ld4(wchunk(wp, r, 5), w + 4);
+      unp_words<8>(w, v, k10);
     }
-    inverse_lift<LEN>(v);
-    if (LEN == 16) {
-      sts128(row, pack16(v[0], v[1]), pack16(v[2], v[3]), pack16(v[4], v[5]), pack16(v[6], v[7]));
-      sts128(row ^ 16, pack16(v[8], v[9]), pack16(v[10], v[11]), pack16(v[12], v[13]), pack16(v[14], v[15]));
-    } else if (LEN == 8) {
-      sts128(row, pack16(v[0], v[1]), pack16(v[2], v[3]), pack16(v[4], v[5]), pack16(v[6], v[7]));
-    } else if (LEN == 4) {
-      sts64(row, pack16(v[0], v[1]), pack16(v[2], v[3]));
+    ld4(wchunk(wp, r, 6), w); ld4(wchunk(wp, r, 7), w + 4);
+    unp_words<8>(w, v + 16, k10);
+  } else if constexpr (LEN == 16) {
+    uint32_t w[8];
+    if (r < 8) {
+      ld4(wchunk(wp, r, 0), v); ld4(wchunk(wp, r, 1), v + 4);
+      ld4(wchunk(wp, r, 5), w);
+      uint32_t w4[4] = {w[0], w[1], w[2], w[3]};
+      unp_words<4>(w4, v + 8, k10);
     } else {
-      sts32(row, pack16(v[0], v[1]));
+      ld4(wchunk(wp, r, 4), w); ld4(wchunk(wp, r, 5), w + 4);
+      unp_words<8>(w, v, k10);
+    }
+  } else if constexpr (LEN == 8) {
+    uint32_t w[4];
+    if (r < 4) {
+      ld4(wchunk(wp, r, 0), v);
+      ld2(wchunk(wp, r, 4) + 8, w);
+      uint32_t w2[2] = {w[0], w[1]};
+      unp_words<2>(w2, v + 4, k10);
+    } else {
+      ld4(wchunk(wp, r, 4), w);
+      unp_words<4>(w, v, k10);
+    }
+  } else if constexpr (LEN == 4) {
+    uint32_t w[2];
+    if (r < 2) {
+      ld2(wchunk(wp, r, 0), v);
+      uint32_t w1[1] = {lds32(wchunk(wp, r, 4) + 4)};
+      unp_words<1>(w1, v + 2, k10);
+    } else {
+      ld2(wchunk(wp, r, 4), w);
+      unp_words<2>(w, v, k10);
+    }
+  } else {  // LEN == 2: the 2x2 corner is all raw (its [0][0] is the tile's DC coefficient)
+    uint32_t w1[1] = {lds32(wchunk(wp, r, 4))};
+    unp_words<1>(w1, v, k10);
+  }
+}
+template <int LEN>
+__device__ __forceinline__ void store_row(uint32_t wp, uint32_t r, const uint32_t (&v)[LEN]) {
+  if constexpr (LEN >= 4) {
+#pragma unroll
+    for (int j = 0; j < LEN / 4; ++j) sts128(wchunk(wp, r, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    sts64(wchunk(wp, r, 0), v[0], v[1]);
+  }
+}
+// column c of a plane: byte offsets of word (i, c) for i & 7 = 0..7 (add i * 128)
+__device__ __forceinline__ void col_offsets(uint32_t c, uint32_t (&off)[8]) {
+#pragma unroll
+  for (int s = 0; s < 8; ++s) off[s] = ((((c >> 2) ^ s) & 7) << 4) + (c & 3) * 4;
+}
+
+// One level (LEN = 2..16) of all three plane pairs: row pass with lane = (plane pair, row), then
+// column pass with lane = (plane pair, column).
+template <int LEN>
+__device__ __forceinline__ void low_level_p(uint32_t w_s, uint32_t lane, uint32_t k10, const ShiftK &sk) {
+  constexpr int ITEMS = 3 * LEN;
+#pragma unroll 1  // (code size: the kernel has to stay inside the 32 KiB L1.5 instruction cache)
+  for (int base = 0; base < ITEMS; base += 32) {
+    const uint32_t item = base + lane;
+    if (item < ITEMS) {
+      const uint32_t wp = w_s + (item / LEN) * kWPlane, r = item % LEN;
+      uint32_t v[LEN];
+      load_row<LEN>(wp, r, v, k10);
+      // low band: the previous level's result (bias kBias) in rows < LEN / 2, raw coefficients below
+      inverse_lift_p<LEN, kRaw>(v, (LEN > 2 && r < LEN / 2) ? pk(2048) : pk(2048 + kBias - kRaw), sk);
+      store_row<LEN>(wp, r, v);
     }
   }
   __syncwarp();
-  // columns
-  if (rc < LEN) {
-    const uint32_t col[2] = {wl + (((rc >> 3) ^ 0) << 4) + (rc & 7) * 2, wl + (((rc >> 3) ^ 1) << 4) + (rc & 7) * 2};
-    int v[LEN];
+#pragma unroll 1  // (code size: the kernel has to stay inside the 32 KiB L1.5 instruction cache)
+  for (int base = 0; base < ITEMS; base += 32) {
+    const uint32_t item = base + lane;
+    if (item < ITEMS) {
+      const uint32_t wp = w_s + (item / LEN) * kWPlane, c = item % LEN;
+      uint32_t off[8];
+      col_offsets(c, off);
+      uint32_t v[LEN];
 #pragma unroll
-    for (int i = 0; i < LEN; ++i) v[i] = lds_s16(col[(i >> 2) & 1] + i * 32);
-    inverse_lift<LEN>(v);
+      for (int i = 0; i < LEN; ++i) v[i] = lds32(wp + off[i & 7] + i * 128);
+      inverse_lift_p<LEN, kBias>(v, pk(2048), sk);
 #pragma unroll
-    for (int i = 0; i < LEN; ++i) sts16(col[(i >> 2) & 1] + i * 32, static_cast<uint32_t>(v[i]));
+      for (int i = 0; i < LEN; ++i) sts32(wp + off[i & 7] + i * 128, v[i]);
+    }
   }
   __syncwarp();
 }
 
-// codec/assemble.cl:39-62: YCoCg667 -> RGB565 with truncating division and an unmasked pack.
-__device__ __forceinline__ void ycocg_to_rgb(int y, int co, int cg, int &r, int &g, int &b) {
-  const int t = y - (cg / 2);
-  g = cg + t;
-  b = (t - co) / 2;
-  r = b + co;
+// codec/assemble.cl:39-62 for both endpoints at once: YCoCg667 -> RGB565 with truncating division and
+// an unmasked shift/or pack.  Inputs: (int8 value + 128) of plane A | plane B << 16.
+//   t = y - cg / 2;  g = cg + t;  b = (t - co) / 2;  r = b + co;  out = r << 11 | g << 5 | b  (low 16 bits)
+// Outputs (per half): R = r + 512, G = g + 2048, Bq = b + 32768.
+__device__ __forceinline__ void ycocg_to_rgb_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk, uint32_t &R, uint32_t &G,
+                                               uint32_t &Bq) {
+  const uint32_t Tn = fma_sub_from(CG, pk(384));                      // -cg + 256; trunc(-cg / 2) = -trunc(cg / 2)
+  const uint32_t n1 = ~(Tn >> 8) & kOnes;                             // [-cg < 0]
+  const uint32_t X1 = mulhi(fma_add(Tn, n1) & 0xFFFEFFFEu, sk.k31);   // trunc(-cg / 2) + 128
+  const uint32_t Tb = fma_add(Y, X1);                                 // (y + 128) + ... = t + 256
+  G = CG + Tb + pk(2048 - 128 - 256);
+  const uint32_t V = Tb - CO + pk(512 - 256 + 128);                   // (t - co) + 512
+  const uint32_t n2 = ~(V >> 9) & kOnes;
+  const uint32_t X2 = mulhi(fma_add(V, n2) & 0xFFFEFFFEu, sk.k31);    // trunc((t - co) / 2) + 256
+  Bq = fma_add(X2, pk(32768 - 256));
+  R = Bq + CO + pk(512 - 32768 - 128);
 }
-__device__ __forceinline__ uint32_t pack565(int y, int co, int cg) {  // low 16 bits valid
-  int r, g, b;
-  ycocg_to_rgb(y, co, cg, r, g, b);
-  return (static_cast<uint32_t>(r) << 11) | (static_cast<uint32_t>(g) << 5) | static_cast<uint32_t>(b);
-}
-
-// 4 sign-extended bytes of a word
-__device__ __forceinline__ void sext4(uint32_t w, int (&o)[4]) {
-  o[0] = sext_byte<0>(w); o[1] = sext_byte<1>(w); o[2] = sext_byte<2>(w); o[3] = sext_byte<3>(w);
+__device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk) {  // ep1 | ep2 << 16
+  uint32_t R, G, Bq;
+  ycocg_to_rgb_p(Y, CO, CG, sk, R, G, Bq);
+  uint32_t rs, gs;
+  asm("mul.lo.u32 %0, %1, 2048;" : "=r"(rs) : "r"(R));  // << 11 and << 5 on the FMA pipe
+  asm("mul.lo.u32 %0, %1, 32;" : "=r"(gs) : "r"(G));
+  return (rs & 0xF800F800u) | (gs & 0xFFE0FFE0u) | (Bq ^ 0x80008000u);
 }
 
 // ---------------------------------------------------------------------------------------
-// Stages 4 + 5.  One warp per 32x32 tile (1024 DXT blocks) of one image, through all six
-// planes [Y1,Y2,Co1,Cg1,Co2,Cg2] (codec/assemble.cl:27-37); warps share nothing, so there is no
-// CTA barrier at all.
-//   wavelet : per plane pair, levels 2..16 on both planes at once (lane = plane x row, then
-//             plane x column), then level 32 per plane (lane = row in registers, then lane =
-//             column); the (char)-truncated result goes to `res`.  The coefficients come
-//             straight from sym_t into registers as 16-byte pieces (rans_streams_kernel):
-//             row r of tile t' of a plane-group is run 4t' + r/8, pieces 2(r%8) and 2(r%8)+1.
+// Stages 4 + 5.  One warp per 32x32 tile (1024 DXT blocks) of one image, all six planes as three
+// plane pairs [Y1|Y2, Co1|Co2, Cg1|Cg2] (codec/assemble.cl:27-37); warps share nothing, so there is
+// no CTA barrier at all.
+//   fetch   : the tile's coefficients, 3 x 2 KiB, cp.async from sym_t into the raw halves of the W
+//             rows: row r of tile tq of a pair-group is the 32-byte pieces k = 2 (r % 8), 2 (r % 8) + 1
+//             of run 4 tq + r / 8 (rans_streams_kernel)
+//   wavelet : levels 2..16 of the three pairs together (lane = pair x row, then pair x column), level 32
+//             per pair (lane = row with the 32 packed coefficients in registers, then lane = column);
+//             the (char)-truncated result replaces W
 //   assembly: 4 DXT1 blocks (or 64 RGB8 texels) per lane and 4-row slab, coalesced 16-byte
 //             stores; palette index = run_end - S.  The index / palette loads of the next slab
 //             are in flight while a slab is assembled, those of slab 0 during the wavelet.
-constexpr int kWaWarps = 4;
-constexpr int kWaSmem = kWaWarps * kWarpWork;  // 36864
+constexpr int kWaWarps = 2;
+constexpr int kWaSmem = kWaWarps * kWarpWork;  // 24576
 
-template <int RGB>
-__global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(const BatchParams p) {
+template <int RGB, bool TAP>
+__global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(const BatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
-  const uint32_t wl_s = w_s + kWBytes;
-  const uint32_t res_s = wl_s + kWlowBytes;
   const uint32_t tiles_per_image = p.n_blocks / kTileSyms;
   const uint32_t gt_tile = blockIdx.x * kWaWarps + warp;  // tile index over the whole batch
   const uint32_t b = gt_tile / tiles_per_image;
@@ -681,8 +839,26 @@ __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(cons
   const uint32_t tile = gt_tile % tiles_per_image;
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
-  // out_off[4b..4b+3] of this image (codec/decoder.cpp:430-463): requested now, first used after
-  // the first plane pair, so the warp never waits for it
+
+  // ---- the tile's coefficients: sym_t -> raw halves of the W rows -------------------------------
+  {
+    const uint32_t tq = tile & 7;
+    const uint8_t *src0 = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(tile >> 3) * (2 * kGroupSyms);
+    const size_t pair_stride = static_cast<size_t>(p.groups_per_plane) * (2 * kGroupSyms);  // = 2N
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t pc = lane + 32 * i, r = pc >> 2, j = pc & 3;
+        cp_async16(wchunk(w_s + pl * kWPlane, r, 4 + j),
+                   src0 + pl * pair_stride + (2 * (r & 7) + (j >> 1)) * 1024 + (4 * tq + (r >> 3)) * 32 + (j & 1) * 16);
+      }
+    }
+    cp_async_commit();
+  }
+
+  // out_off[4b..4b+3] of this image (codec/decoder.cpp:430-463): requested now, first used after the
+  // lower wavelet levels, so the warp never waits for it
   const uint4 out_off = __ldg(reinterpret_cast<const uint4 *>(p.cmp) + b);
   uint32_t n_entries = 0;
   bool pal_ok = false;
@@ -697,21 +873,29 @@ __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(cons
   const uint32_t slab_stride = 4 * p.blocks_x;
   // S of 4 blocks (raw) + the run end; words = the 4 palette words
   struct Sfx { uint4 raw; uint32_t re; };
-  auto load_sfx = [&](uint32_t gidx) -> Sfx {
-    // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
+  // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
+  auto sfx_ptr = [&](uint32_t gidx) -> const uint8_t * {
     const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
+    return reinterpret_cast<const uint8_t *>(p.idx_s) + (idx16 ? 2 * e : 4 * e);
+  };
+  auto load_sfx = [&](uint32_t gidx) -> Sfx {
+    const uint8_t *sp = sfx_ptr(gidx);
     Sfx r;
     if (idx16) {
-      const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(p.idx_s) + e));
+      const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(sp));
       r.raw = make_uint4(sv.x, sv.y, 0u, 0u);
     } else {
-      r.raw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.idx_s) + e));
+      r.raw = __ldg(reinterpret_cast<const uint4 *>(sp));
     }
     r.re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
     return r;
   };
-  uint32_t word_nx[4] = {0u, 0u, 0u, 0u};
-  auto load_words = [&](const Sfx &sf, uint32_t gidx) {
+  // the suffix sums come from DRAM (the rANS kernel wrote them): pull them into L1 two slabs before
+  // they are loaded, so that the load -> index -> palette gather chain of a slab starts on time
+  auto prefetch_sfx = [&](uint32_t gidx) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(sfx_ptr(gidx)));
+  };
+  auto load_words = [&](const Sfx &sf, uint32_t gidx, uint32_t (&word)[4]) {
     uint32_t sfx[4];
     if (idx16) {
       sfx[0] = sf.raw.x & 0xFFFFu; sfx[1] = sf.raw.x >> 16; sfx[2] = sf.raw.y & 0xFFFFu; sfx[3] = sf.raw.y >> 16;
@@ -723,149 +907,99 @@ __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(cons
     for (int j = 0; j < 4; ++j) {
       idx[j] = sf.re - sfx[j];
       if (idx16) idx[j] &= 0xFFFFu;
-      word_nx[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
+      word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
     }
-    if (p.tap_indices)
+    if (TAP && p.tap_indices)
       *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
   };
-
-  // ---- the tile's coefficients: sym_t -> res, one cp.async group per plane pair ------------------
-  // 16-byte piece (row r, half j) of tile tq of a plane-group sits at [k = 2 (r % 8) + j][run 4 tq + r / 8]
-  // (rans_streams_kernel); res[plane] receives the tile row-major, and later its int8 result.
-  {
-    const uint32_t tq = tile & 7;
-    const uint8_t *src0 = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(tile >> 3) * kGroupSyms;
-    const size_t plane_stride = static_cast<size_t>(p.groups_per_plane) * kGroupSyms;  // = N
-#pragma unroll
-    for (int pl = 0; pl < 6; ++pl) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t pc = lane + 32 * i, r = pc >> 1, j = pc & 1;
-        cp_async16(res_s + pl * kTileSyms + pc * 16,
-                   src0 + pl * plane_stride + (2 * (r & 7) + j) * 512 + (4 * tq + (r >> 3)) * 16);
-      }
-      if (pl & 1) cp_async_commit();
-    }
-  }
+  // software pipeline of the assembly inputs: the palette words of slab k + 1 are gathered while slab k
+  // is assembled, from suffix sums loaded two slabs earlier and prefetched into L1 two slabs before that
   Sfx sa = load_sfx(gidx0), sb = load_sfx(gidx0 + slab_stride);
+  prefetch_sfx(gidx0 + 2 * slab_stride);
+  prefetch_sfx(gidx0 + 3 * slab_stride);
 
   // ---- stage 4: inverse wavelet ------------------------------------------------------------
-  const uint32_t wl = wl_s + (lane >> 4) * 512;
+  uint32_t k10 = 0x10101010u;
+  asm volatile("" : "+r"(k10));  // keep it in a register (PRMT takes no immediate source)
+  cp_async_wait_group<0>();
+  __syncwarp();
+  const ShiftK sk{1u << 30, 1u << 31};
+  low_level_p<2>(w_s, lane, k10, sk);
+  low_level_p<4>(w_s, lane, k10, sk);
+  low_level_p<8>(w_s, lane, k10, sk);
+  low_level_p<16>(w_s, lane, k10, sk);
 
-#pragma unroll 1
-  for (uint32_t pair = 0; pair < 3; ++pair) {
-    if (pair == 0) cp_async_wait_group<2>();
-    else if (pair == 1) cp_async_wait_group<1>();
-    else cp_async_wait_group<0>();
-    __syncwarp();
-    // corners: lane -> (plane 2 pair + lane/16, row lane%16), bytes -> (byte - 128) as int16
-    {
-      const uint32_t r = lane & 15;
-      const uint4 c = lds128(res_s + (2 * pair + (lane >> 4)) * kTileSyms + r * 32);
-      const uint32_t x0 = c.x ^ 0x80808080u, x1 = c.y ^ 0x80808080u, x2 = c.z ^ 0x80808080u, x3 = c.w ^ 0x80808080u;
-      const uint32_t row = wl + r * 32 + (((r >> 2) & 1) << 4);
-      sts128(row, sext_byte_pair<0>(x0), sext_byte_pair<2>(x0), sext_byte_pair<0>(x1), sext_byte_pair<2>(x1));
-      sts128(row ^ 16, sext_byte_pair<0>(x2), sext_byte_pair<2>(x2), sext_byte_pair<0>(x3), sext_byte_pair<2>(x3));
-    }
-    __syncwarp();
-    low_level<2>(wl, lane);
-    low_level<4>(wl, lane);
-    low_level<8>(wl, lane);
-    low_level<16>(wl, lane);
+  uint32_t word_nx[4];  // palette words of the next slab
+  {  // slab 0: indices -> palette words;  slabs 1, 2: suffix sums in registers
+    const uint32_t palette_bytes = out_off.w - out_off.z;
+    const uint32_t pal_off = out_off.z - 7u * p.n_blocks * b - 6u * p.n_blocks;  // compact palette scratch
+    n_entries = palette_bytes / 4;
+    pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
+    pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? pal_off : 0));
+    load_words(sa, gidx0, word_nx);
+    sa = sb;
+    sb = load_sfx(gidx0 + 2 * slab_stride);
+    prefetch_sfx(gidx0 + 4 * slab_stride);
+  }
 
+  // level 32, rows: lane = row
 #pragma unroll 1
-    for (uint32_t q = 0; q < 2; ++q) {
-      const uint32_t pl = 2 * pair + q;
-      const uint32_t rs = res_s + pl * kTileSyms;
-      // ---- level 32, rows: lane = row
-      {
-        int v[32];
-        if (lane < 16) {  // low half of rows 0..15 = the 16x16 result of the lower levels
-          const uint32_t row = wl_s + q * 512 + lane * 32 + (((lane >> 2) & 1) << 4);
-          const uint4 a = lds128(row), c = lds128(row ^ 16);
-          const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  for (uint32_t pl = 0; pl < 3; ++pl) {
+    const uint32_t wp = w_s + pl * kWPlane;
+    uint32_t v[32];
+    load_row<32>(wp, lane, v, k10);
+    inverse_lift_p<32, kRaw>(v, lane < 16 ? pk(2048) : pk(2048 + kBias - kRaw), sk);
+    store_row<32>(wp, lane, v);
+  }
+  __syncwarp();
+  // level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
+  {
+    uint32_t off[8];
+    col_offsets(lane, off);
+#pragma unroll 1
+    for (uint32_t pl = 0; pl < 3; ++pl) {
+      const uint32_t wp = w_s + pl * kWPlane;
+      uint32_t v[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { v[2 * i] = lo16(w[i]); v[2 * i + 1] = hi16(w[i]); }
-        } else {
-          const uint4 a = lds128(rs + lane * 32);
-          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, a.z ^ 0x80808080u, a.w ^ 0x80808080u};
+      for (int i = 0; i < 32; ++i) v[i] = lds32(wp + off[i & 7] + i * 128);
+      inverse_lift_p<32, kBias>(v, pk(2048), sk);
+      // (char) truncation: low byte of (x + 4096) = x mod 256; ^ 0x80 makes it (int8) x + 128
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[4 * i] = sext_byte<0>(x[i]); v[4 * i + 1] = sext_byte<1>(x[i]);
-            v[4 * i + 2] = sext_byte<2>(x[i]); v[4 * i + 3] = sext_byte<3>(x[i]);
-          }
-        }
-        {
-          const uint4 a = lds128(rs + lane * 32 + 16);
-          const uint32_t x[4] = {a.x ^ 0x80808080u, a.y ^ 0x80808080u, a.z ^ 0x80808080u, a.w ^ 0x80808080u};
+      for (int i = 0; i < 32; ++i) sts32(wp + off[i & 7] + i * 128, (v[i] & 0x00FF00FFu) ^ 0x00800080u);
+      if (TAP && p.tap_planes) {
+        // reference plane order [Y1, Y2, Co1, Cg1, Co2, Cg2]: pair 0 = planes (0, 1), pair 1 = (2, 4), pair 2 = (3, 5)
+        const uint32_t pa = pl == 0 ? 0 : pl == 1 ? 2 : 3, pb = pl == 0 ? 1 : pl == 1 ? 4 : 5;
+        int8_t *t0 = p.tap_planes + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[16 + 4 * i] = sext_byte<0>(x[i]); v[16 + 4 * i + 1] = sext_byte<1>(x[i]);
-            v[16 + 4 * i + 2] = sext_byte<2>(x[i]); v[16 + 4 * i + 3] = sext_byte<3>(x[i]);
-          }
-        }
-        inverse_lift<32>(v);
-        const uint32_t wrow = w_s + lane * 64 + (((lane >> 1) & 3) << 4);  // logical chunk 0
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          sts128(wrow ^ (j << 4), pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
-                 pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
-      }
-      __syncwarp();  // W complete, and every lane is done with the plane's coefficients in res
-      // ---- level 32, columns: lane = column; (char) truncation (codec/inverse_wavelet.cl:188-190)
-      {
-        uint32_t col[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) col[s] = w_s + ((((lane >> 3) ^ s) & 3) << 4) + (lane & 7) * 2;
-        int v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lds_s16(col[(i >> 1) & 3] + i * 64);
-        inverse_lift<32>(v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sts8(rs + lane + i * 32, static_cast<uint32_t>(v[i]));
-        if (p.tap_planes) {
-          int8_t *tp = p.tap_planes + (static_cast<size_t>(b) * 6 + pl) * p.n_blocks +
-                       static_cast<size_t>(ty * kTile) * p.blocks_x + tx * kTile + lane;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tp[static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i]);
+        for (int i = 0; i < 32; ++i) {
+          t0[static_cast<size_t>(pa) * p.n_blocks + static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>(v[i] & 0xFFu);
+          t0[static_cast<size_t>(pb) * p.n_blocks + static_cast<size_t>(i) * p.blocks_x] = static_cast<int8_t>((v[i] >> 16) & 0xFFu);
         }
       }
-      __syncwarp();
-    }
-    if (pair == 0) {  // slab 0: indices -> palette words;  slabs 1, 2: suffix sums in flight
-      const uint32_t palette_bytes = out_off.w - out_off.z;
-      const uint32_t pal_off = out_off.z - 7u * p.n_blocks * b - 6u * p.n_blocks;  // compact palette scratch
-      n_entries = palette_bytes / 4;
-      pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
-      pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? pal_off : 0));
-      load_words(sa, gidx0);
-      sa = sb;
-      sb = load_sfx(gidx0 + 2 * slab_stride);
     }
   }
+  __syncwarp();
 
   // ---- stage 5: assembly, codec/assemble.cl:64-129 ---------------------------------------
 #pragma unroll 1
   for (uint32_t k = 0; k < 8; ++k) {
     const uint32_t gidx = gidx0 + k * slab_stride;
     const uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
-    if (k + 1 < 8) load_words(sa, gidx + slab_stride);  // its S / run end were requested two slabs ago
+    if (k + 1 < 8) load_words(sa, gidx + slab_stride, word_nx);  // its S / run end were loaded two slabs ago
     sa = sb;
     if (k + 3 < 8) sb = load_sfx(gidx + 3 * slab_stride);
-    const uint32_t src = res_s + k * 128 + lane * 4;  // rows 4k..4k+3 of the tile, 4 bytes per lane
-    uint32_t pw[6];
-#pragma unroll
-    for (int pl = 0; pl < 6; ++pl) pw[pl] = lds32(src + pl * kTileSyms);
-
-    int y1[4], y2[4], co1[4], cg1[4], co2[4], cg2[4];
-    sext4(pw[0], y1); sext4(pw[1], y2); sext4(pw[2], co1); sext4(pw[3], cg1); sext4(pw[4], co2); sext4(pw[5], cg2);
+    if (k + 5 < 8) prefetch_sfx(gidx + 5 * slab_stride);
+    // rows 4k..4k+3 of the tile, 4 blocks per lane: (int8 + 128) of plane A | plane B << 16
+    const uint32_t src = wchunk(w_s, 4 * k + (lane >> 3), lane & 7);
+    uint32_t Y[4], CO[4], CG[4];
+    ld4(src, Y); ld4(src + kWPlane, CO); ld4(src + 2 * kWPlane, CG);
 
     if (!RGB) {
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         // PhysicalDXTBlock (codec/dxt_image.h:14-21): u16 ep1, u16 ep2, u32 interpolation
-        o[2 * j] = __byte_perm(pack565(y1[j], co1[j], cg1[j]), pack565(y2[j], co2[j], cg2[j]), 0x5410);
+        o[2 * j] = pack565_p(Y[j], CO[j], CG[j], sk);
         o[2 * j + 1] = word[j];
       }
       uint8_t *dst = p.out + (img_block0 + gidx) * 8;
@@ -877,9 +1011,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 6) wavelet_assemble_kernel(cons
       uint32_t pal4[4][4];  // [block j][palette entry] = r | g << 8 | b << 16 (uchar-truncated)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int c0[3], c1[3];
-        ycocg_to_rgb(y1[j], co1[j], cg1[j], c0[0], c0[1], c0[2]);
-        ycocg_to_rgb(y2[j], co2[j], cg2[j], c1[0], c1[1], c1[2]);
+        uint32_t R, G, Bq;
+        ycocg_to_rgb_p(Y[j], CO[j], CG[j], sk, R, G, Bq);
+        int c0[3] = {static_cast<int>(R & 0xFFFFu) - 512, static_cast<int>(G & 0xFFFFu) - 2048, static_cast<int>(Bq & 0xFFFFu) - 32768};
+        int c1[3] = {static_cast<int>(R >> 16) - 512, static_cast<int>(G >> 16) - 2048, static_cast<int>(Bq >> 16) - 32768};
         c0[0] = static_cast<int>((static_cast<uint32_t>(c0[0]) << 3) | static_cast<uint32_t>(c0[0] >> 2));
         c0[1] = static_cast<int>((static_cast<uint32_t>(c0[1]) << 2) | static_cast<uint32_t>(c0[1] >> 4));
         c0[2] = static_cast<int>((static_cast<uint32_t>(c0[2]) << 3) | static_cast<uint32_t>(c0[2] >> 2));
@@ -950,10 +1085,11 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
   if (group >= n_groups) return;
   uint8_t *dst = out + (static_cast<size_t>(group) * n_lanes + lane) * kSymsPerLane + 240;
   const bool active = lane < n_lanes;
-  rans_decode_groups<false, 1>(tab_s, data, group, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
-                           [&](int, int m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                             if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w0, w1, w2, w3);
-                           });
+  const uint32_t grp[1] = {group};
+  rans_decode_groups<false, 1, false>(tab_s, data, grp, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
+                                      [&](int m, const uint32_t (&w)[4]) {
+                                        if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w[0], w[1], w[2], w[3]);
+                                      });
 }
 
 }  // namespace
@@ -969,12 +1105,14 @@ cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_
 
 static cudaError_t ensure_attrs() {
   static cudaError_t once = []() {
-    cudaError_t e = cudaFuncSetAttribute(wavelet_assemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(wavelet_assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rans_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRansSmem);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    for (auto *k : {wavelet_assemble_kernel<0, false>, wavelet_assemble_kernel<1, false>, wavelet_assemble_kernel<0, true>,
+                    wavelet_assemble_kernel<1, true>}) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem)) != cudaSuccess) return e;
+    }
+    for (auto *k : {rans_streams_kernel<false>, rans_streams_kernel<true>}) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kRansSmem)) != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(ans_decode_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem);
   }();
   return once;
@@ -994,11 +1132,16 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
   StreamGrid sg;
-  sg.y_ctas = (2 * p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
-  sg.c_ctas = (4 * p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
+  sg.y_ctas = (p.groups_per_plane + kRansWarps - 1) / kRansWarps;      // one (plane pair, group) per warp
+  sg.c_ctas = (2 * p.groups_per_plane + kRansWarps - 1) / kRansWarps;
   sg.pal_ctas = (max_palette_bytes / kGroupSyms + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
   sg.idx_ctas = (p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
-  rans_streams_kernel<<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
+  // the stage taps (parity tests only) are a separate instantiation: the production kernels carry none of that code
+  const bool taps = p.tap_symbols || p.tap_planes || p.tap_indices;
+  if (taps)
+    rans_streams_kernel<true><<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
+  else
+    rans_streams_kernel<false><<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
@@ -1009,10 +1152,14 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   // stages 4 + 5: one warp per tile
   const uint64_t tiles = static_cast<uint64_t>(p.n_images) * (p.n_blocks / kTileSyms);
   const uint32_t grid = static_cast<uint32_t>((tiles + kWaWarps - 1) / kWaWarps);
-  if (rgb_mode)
-    wavelet_assemble_kernel<1><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
+  if (rgb_mode && taps)
+    wavelet_assemble_kernel<1, true><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
+  else if (rgb_mode)
+    wavelet_assemble_kernel<1, false><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
+  else if (taps)
+    wavelet_assemble_kernel<0, true><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
   else
-    wavelet_assemble_kernel<0><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
+    wavelet_assemble_kernel<0, false><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return stamp();
