@@ -126,7 +126,7 @@ __device__ __forceinline__ void cp_async_wait_group() {
 // same stream in one interleaved instruction stream: the decode step is a chain of ~12 dependent
 // instructions (two of them shared-memory loads), and two independent chains per warp hide
 // that latency better than twice the warps would (registers, not warps, are what is left).
-// Chain c uses the ring at ring_s + c * kRing.
+// Chain c uses the ring at ring[c].
 // emit(m, acc): called 16 times; acc holds the 16 symbols at positions q0 = 240 - 16m .. q0 + 15 of
 // this lane's 256-symbol run of every chain:
 //   ILV = false: acc[4c + j] = symbols q0 + 4j .. q0 + 4j + 3 of chain c, little-endian packed
@@ -136,7 +136,7 @@ __device__ __forceinline__ void cp_async_wait_group() {
 //                PRMT that files a symbol away takes any destination byte.
 template <bool FULL, int NC, bool ILV, class Emit>
 __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t *__restrict__ stream,
-                                                   const uint32_t (&grp)[NC], uint32_t n_lanes, uint32_t ring_s,
+                                                   const uint32_t (&grp)[NC], uint32_t n_lanes, const uint32_t (&ring)[NC],
                                                    const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
   static_assert(!ILV || NC == 2, "interleaved output needs two chains");
   const uint32_t lane = threadIdx.x & 31;
@@ -168,7 +168,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
     for (int i = 0; i < kRing / kChunk; ++i) {
       const uintptr_t a = lo[c] + 16 * lane + kChunk * i;
       if (a >= lo16 && a + 16 <= hi16)
-        cp_async16(ring_s + c * kRing + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+        cp_async16(ring[c] + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
     }
     pos[c] = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
     mprev[c] = 0u;
@@ -202,7 +202,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
           lo[c] -= kChunk;
           const uintptr_t a = lo[c] + 16 * lane;
           if (a >= lo16 && a + 16 <= hi16)
-            cp_async16(ring_s + c * kRing + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+            cp_async16(ring[c] + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
         }
       }
       cp_async_commit();
@@ -212,9 +212,11 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
       for (int k = 0; k < 8; ++k) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const uint32_t slot = state[c] & (kTableSize - 1);
-          uint32_t slot_a;  // tab_s + 4 * slot
-          asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(slot_a) : "r"(slot), "r"(tab_s));
+          // tab_s | ((state << 2) & 0x1FFC): the shift as a multiply on the FMA pipe, one LOP3 (the table is
+          // 8 KiB-aligned in the shared window) -- the mask-then-scale form costs two ALU-pipe instructions
+          uint32_t s4, slot_a;
+          asm("mul.lo.u32 %0, %1, 4;" : "=r"(s4) : "r"(state[c]));
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(slot_a) : "r"(s4), "n"(4 * kTableSize - 4), "r"(tab_s));
           const uint32_t e = lds32(slot_a);
           // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  The shifts of freq and symbol
           // are written as multiplies so that they issue on the FMA pipe.  The multiply-high is left to
@@ -233,7 +235,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
           pos[c] -= 2u * __popc(sel);
           mprev[c] = mask;
           uint32_t ra;  // (pos & (kRing - 1)) | ring in one LOP3 (the ring is kRing-aligned)
-          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(pos[c]), "n"(kRing - 1), "r"(ring_s + c * kRing));
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(pos[c]), "n"(kRing - 1), "r"(ring[c]));
           const uint32_t w = lds_u16(ra);
           uint32_t renorm;  // state << 16 | w
           asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state[c]), "r"(w));
@@ -375,6 +377,22 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 //       when every palette of the batch has <= 65536 entries (idx < 2^16 then makes the 16-bit
 //       difference exact), else as 32 bits, in the same transposed order as sym_t:
 //       [group][k][lane][16 values].
+// Shared-memory layout of a decode CTA: n 2 KiB rings and the 8 KiB table.  The rings are indexed by OR-ing
+// low address bits into their base and so is the table, so they must be aligned to their size; the
+// dynamic shared window is only guaranteed 1 KiB alignment.  The table goes to the first 8 KiB boundary,
+// the rings fill the 2 KiB slots before and after it: n * 2 KiB + 8 KiB + at most 2 KiB of slack.
+struct RansSmem {
+  uint32_t s0, tab, n_before;
+  __device__ __forceinline__ explicit RansSmem(uint32_t base) {
+    s0 = (base + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
+    tab = (s0 + 4 * kTableSize - 1) & ~static_cast<uint32_t>(4 * kTableSize - 1);
+    n_before = (tab - s0) / kRing;
+  }
+  __device__ __forceinline__ uint32_t ring(uint32_t i) const {
+    return i < n_before ? s0 + i * kRing : tab + 4 * kTableSize + (i - n_before) * kRing;
+  }
+};
+
 constexpr int kRansWarps = 8;
 constexpr int kRansChains = 2;                          // rANS groups per warp
 constexpr int kRansGroupsPerCta = kRansWarps * kRansChains;
@@ -393,14 +411,14 @@ struct StreamGrid {
 // chroma = Co1 || Cg1 || Co2 || Cg2, every plane groups_per_plane groups long.
 template <bool TAP>
 __device__ __forceinline__ void rans_plane_pair(const BatchParams &p, uint32_t b, uint32_t pair, uint32_t g,
-                                                const uint8_t *stream, uint32_t out_off, uint32_t tab_s, uint32_t ring_s) {
+                                                const uint8_t *stream, uint32_t out_off, uint32_t tab_s, const uint32_t (&ring)[2]) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gpp = p.groups_per_plane;
   const uint32_t grp[2] = {pair == 2 ? gpp + g : g, pair == 0 ? gpp + g : pair == 1 ? 2 * gpp + g : 3 * gpp + g};
   uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + lane * kSymsPerLane + 240 : nullptr;
   uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + (static_cast<size_t>(pair) * gpp + g) * (2 * kGroupSyms) +
                  15 * 1024 + lane * 32;
-  rans_decode_groups<true, 2, true>(tab_s, stream, grp, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+  rans_decode_groups<true, 2, true>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                     [&](int m, const uint32_t (&w)[8]) {
                                       *reinterpret_cast<uint4 *>(dst - 1024 * m) = make_uint4(w[0], w[1], w[2], w[3]);
                                       *reinterpret_cast<uint4 *>(dst - 1024 * m + 16) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -420,9 +438,12 @@ __device__ __forceinline__ void rans_plane_pair(const BatchParams &p, uint32_t b
 template <int NC, bool TAP>
 __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_t b, uint32_t type, uint32_t group,
                                                    const uint8_t *stream, uint32_t out_off, uint32_t pal_off,
-                                                   uint32_t tab_s, uint32_t ring_s) {
+                                                   uint32_t tab_s, const uint32_t (&ring2)[2]) {
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t grp[NC];
+  uint32_t grp[NC], ring[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) ring[c] = ring2[c];
+
 #pragma unroll
   for (int c = 0; c < NC; ++c) grp[c] = group + c;
   uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane + 240
@@ -431,7 +452,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
     const uint64_t off = static_cast<uint64_t>(pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
     const bool ok = off + NC * kGroupSyms <= p.palette_cap;
     uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
-    rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+    rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                         [&](int m, const uint32_t (&w)[NC * 4]) {
 #pragma unroll
                                           for (int c = 0; c < NC; ++c) {
@@ -450,7 +471,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
   const bool idx16 = p.idx16 != 0;
-  rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring_s, p.cmp, p.cmp + p.cmp_bytes,
+  rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                [&](int m, const uint32_t (&wa)[NC * 4]) {
 #pragma unroll
                                  for (int c = 0; c < NC; ++c) {
@@ -494,12 +515,10 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
 template <bool TAP>
 __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // the rings are indexed by OR-ing low address bits, so they must be kRing-aligned; the dynamic
-  // shared window itself is only guaranteed 1 KiB alignment, hence kRing bytes of slack
-  const uint32_t smem_s = (smem_u32(smem) + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
+  const RansSmem lay(smem_u32(smem));
   const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t ring_s = smem_s + warp * kRansChains * kRing;
-  const uint32_t tab_s = smem_s + kRansGroupsPerCta * kRing;
+  const uint32_t ring[2] = {lay.ring(2 * warp), lay.ring(2 * warp + 1)};
+  const uint32_t tab_s = lay.tab;
 
   const uint32_t per_image = sg.per_image();
   const uint32_t b = blockIdx.x / per_image;
@@ -523,7 +542,7 @@ __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const 
     const uint32_t item = r * kRansWarps + warp;
     if (item >= n_items) return;
     const uint32_t pair = type == 0 ? 0u : 1u + item / p.groups_per_plane;
-    rans_plane_pair<TAP>(p, b, pair, item % p.groups_per_plane, stream, out_off, tab_s, ring_s);
+    rans_plane_pair<TAP>(p, b, pair, item % p.groups_per_plane, stream, out_off, tab_s, ring);
     return;
   }
   const uint32_t n_groups = type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
@@ -534,9 +553,9 @@ __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const 
   const uint32_t group = first + warp * kRansChains;
   if (group >= n_groups) return;
   if (group + 1 < n_groups)
-    rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
+    rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring);
   else
-    rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring_s);
+    rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring);
 }
 
 // The cross-group part of stage 3 (what the collect_indices passes of
@@ -1076,9 +1095,9 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
                             uint64_t data_bytes, uint32_t n_groups, uint32_t n_lanes,
                             uint8_t *__restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t smem_s = (smem_u32(smem) + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
+  const RansSmem lay(smem_u32(smem));
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tab_s = smem_s + kPlainWarps * kRing;
+  const uint32_t tab_s = lay.tab;
   load_table(tab_s, table, threadIdx.x, kPlainWarps * 32);
   __syncthreads();
   const uint32_t group = blockIdx.x * kPlainWarps + warp;
@@ -1086,7 +1105,8 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
   uint8_t *dst = out + (static_cast<size_t>(group) * n_lanes + lane) * kSymsPerLane + 240;
   const bool active = lane < n_lanes;
   const uint32_t grp[1] = {group};
-  rans_decode_groups<false, 1, false>(tab_s, data, grp, n_lanes, smem_s + warp * kRing, data, data + data_bytes,
+  const uint32_t ring[1] = {lay.ring(warp)};
+  rans_decode_groups<false, 1, false>(tab_s, data, grp, n_lanes, ring, data, data + data_bytes,
                                       [&](int m, const uint32_t (&w)[4]) {
                                         if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w[0], w[1], w[2], w[3]);
                                       });
