@@ -232,7 +232,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
           const uint32_t mask = __ballot_sync(0xffffffffu, need);
           uint32_t sel;  // (mask & gt) | (mprev & ~gt)
           asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(sel) : "r"(mask), "r"(mprev[c]), "r"(gt));
-          pos[c] -= 2u * __popc(sel);
+          asm("mad.lo.u32 %0, %1, 0xfffffffe, %0;" : "+r"(pos[c]) : "r"(__popc(sel)));  // pos -= 2 popc, on the FMA pipe
           mprev[c] = mask;
           uint32_t ra;  // (pos & (kRing - 1)) | ring in one LOP3 (the ring is kRing-aligned)
           asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(pos[c]), "n"(kRing - 1), "r"(ring[c]));
