@@ -24,20 +24,25 @@ def main():
     name = rows[start - 1][1] if start else ""
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
     # locate the function: ".text.<mangled>" section whose mangled name matches the regex
-    lines, cur, active, inl = [], None, False, None
+    # every ".text.<mangled>" section whose name matches the regex; the instantiation that was profiled is the
+    # one with as many SASS instructions as the report lists
+    secs, cur, name_m = {}, None, None
     for l in dis:
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
         if m:
-            active = re.search(kre, m.group(1)) is not None and "ILi1" not in m.group(1)
+            name_m = m.group(1) if re.search(kre, m.group(1)) else None
+            if name_m:
+                secs[name_m] = []
             continue
-        if not active:
+        if not name_m:
             continue
         m = re.search(r"//## File \"([^\"]+)\", line (\d+)(.*)", l)
         if m:
             cur = int(m.group(2))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
-            lines.append(cur)
+            secs[name_m].append(cur)
+    lines = min(secs.values(), key=lambda v: abs(len(v) - len(counts))) if secs else []
     if len(lines) != len(counts):
         print(f"warning: {len(lines)} SASS instructions in the cubin, {len(counts)} in the report", file=sys.stderr)
     per = {}
