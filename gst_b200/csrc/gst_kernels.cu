@@ -897,8 +897,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
     return reinterpret_cast<const uint8_t *>(p.idx_s) + (idx16 ? 2 * e : 4 * e);
   };
-  auto load_sfx = [&](uint32_t gidx) -> Sfx {
-    const uint8_t *sp = sfx_ptr(gidx);
+  auto load_sfx_at = [&](const uint8_t *sp, uint32_t gidx) -> Sfx {
     Sfx r;
     if (idx16) {
       const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(sp));
@@ -909,11 +908,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     r.re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
     return r;
   };
+  auto load_sfx = [&](uint32_t gidx) -> Sfx { return load_sfx_at(sfx_ptr(gidx), gidx); };
   // the suffix sums come from DRAM (the rANS kernel wrote them): pull them into L1 two slabs before
   // they are loaded, so that the load -> index -> palette gather chain of a slab starts on time
-  auto prefetch_sfx = [&](uint32_t gidx) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(sfx_ptr(gidx)));
-  };
+  auto prefetch_sfx = [&](const uint8_t *sp) { asm volatile("prefetch.global.L1 [%0];" ::"l"(sp)); };
   auto load_words = [&](const Sfx &sf, uint32_t gidx, uint32_t (&word)[4]) {
     uint32_t sfx[4];
     if (idx16) {
@@ -934,8 +932,9 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   // software pipeline of the assembly inputs: the palette words of slab k + 1 are gathered while slab k
   // is assembled, from suffix sums loaded two slabs earlier and prefetched into L1 two slabs before that
   Sfx sa = load_sfx(gidx0), sb = load_sfx(gidx0 + slab_stride);
-  prefetch_sfx(gidx0 + 2 * slab_stride);
-  prefetch_sfx(gidx0 + 3 * slab_stride);
+  const uint8_t *pf_a = sfx_ptr(gidx0 + 2 * slab_stride), *pf_b = sfx_ptr(gidx0 + 3 * slab_stride);  // prefetched, not yet loaded
+  prefetch_sfx(pf_a);
+  prefetch_sfx(pf_b);
 
   // ---- stage 4: inverse wavelet ------------------------------------------------------------
   uint32_t k10 = 0x10101010u;
@@ -957,8 +956,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? pal_off : 0));
     load_words(sa, gidx0, word_nx);
     sa = sb;
-    sb = load_sfx(gidx0 + 2 * slab_stride);
-    prefetch_sfx(gidx0 + 4 * slab_stride);
+    sb = load_sfx_at(pf_a, gidx0 + 2 * slab_stride);
+    pf_a = pf_b;
+    pf_b = sfx_ptr(gidx0 + 4 * slab_stride);
+    prefetch_sfx(pf_b);
   }
 
   // level 32, rows: lane = row
@@ -1006,8 +1007,12 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     const uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
     if (k + 1 < 8) load_words(sa, gidx + slab_stride, word_nx);  // its S / run end were loaded two slabs ago
     sa = sb;
-    if (k + 3 < 8) sb = load_sfx(gidx + 3 * slab_stride);
-    if (k + 5 < 8) prefetch_sfx(gidx + 5 * slab_stride);
+    if (k + 3 < 8) sb = load_sfx_at(pf_a, gidx + 3 * slab_stride);
+    pf_a = pf_b;
+    if (k + 5 < 8) {
+      pf_b = sfx_ptr(gidx + 5 * slab_stride);
+      prefetch_sfx(pf_b);
+    }
     // rows 4k..4k+3 of the tile, 4 blocks per lane: (int8 + 128) of plane A | plane B << 16
     const uint32_t src = wchunk(w_s, 4 * k + (lane >> 3), lane & 7);
     uint32_t Y[4], CO[4], CG[4];
