@@ -11,6 +11,8 @@ from .decoder import (  # noqa: F401
     Decoder,
     FrameStreamer,
     GenTCHeader,
+    build_gst,
+    encode_stream,
     kANSTableSize,
     kNumEncodedSymbols,
     kThreadsPerEncodingGroup,
@@ -22,7 +24,7 @@ from .decoder import (  # noqa: F401
 )
 
 __all__ = [
-    "AnsDecoder", "Decoder", "FrameStreamer", "GenTCHeader", "GstError", "lib", "load_library",
+    "AnsDecoder", "Decoder", "FrameStreamer", "build_gst", "encode_stream", "GenTCHeader", "GstError", "lib", "load_library",
     "normalize_frequencies", "pack_batch", "parse_header", "required_scratch_mem",
     "kANSTableSize", "kNumEncodedSymbols", "kThreadsPerEncodingGroup", "kWaveletBlockDim",
 ]

@@ -66,6 +66,8 @@ PROTOTYPES = {
     "gst_ans_table": (_int, [_vp, _vp, _vp, _vp]),
     "gst_ans_decode": (_int, [_vp, _u32, C.POINTER(_u32), _pp, C.POINTER(_sz), _u32, _vp]),
     "gst_ans_destroy": (None, [_vp]),
+    "gst_ans_encode_bound": (_sz, [_sz]),
+    "gst_ans_encode_stream": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "gst_build_tables": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "gst_launches_per_batch": (_int, []),
     "gst_profile_enable": (_int, [_vp, _int]),

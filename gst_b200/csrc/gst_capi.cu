@@ -872,6 +872,76 @@ int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t
   return GST_OK;
 }
 
+// ---- rANS stream encoder (fixture tooling) --------------------------------------------------
+size_t gst_ans_encode_bound(size_t n_symbols) {
+  const size_t groups = n_symbols / gst::kGroupSyms;
+  return 4 * groups + groups * (gst::kEncGroupCapBytes + 2) + 4;
+}
+
+int gst_ans_encode_stream(gst_ctx *ctx, const uint8_t *symbols, size_t n_symbols, uint16_t *freqs_out,
+                          uint8_t *stream_out, size_t stream_cap, size_t *stream_bytes) {
+  if (!ctx || !symbols || !freqs_out || !stream_out || !stream_bytes) return fail(GST_ERR_INVALID, "null argument");
+  if (n_symbols == 0 || n_symbols % gst::kGroupSyms) return fail(GST_ERR_INVALID, "n_symbols must be a positive multiple of 8192");
+  if (n_symbols / gst::kGroupSyms > 0x7FFFFFu) return fail(GST_ERR_INVALID, "stream too long for 32-bit offsets");
+  // histogram -> normalised frequencies, codec/entropy.cpp:176-190
+  std::vector<uint32_t> counts(256, 0);
+  for (size_t i = 0; i < n_symbols; ++i) counts[symbols[i]]++;
+  uint32_t nz = 0;
+  for (uint32_t i = 0; i < 256; ++i) if (counts[i]) nz = i + 1;
+  std::vector<uint32_t> F(nz);
+  int rc = gst_normalize_frequencies(counts.data(), nz, 0, F.data());
+  if (rc != GST_OK) return rc;
+  uint16_t f16[256];
+  for (uint32_t i = 0; i < 256; ++i) {
+    f16[i] = i < nz ? static_cast<uint16_t>(F[i]) : 0;
+    if (counts[i] && !f16[i]) return fail(GST_ERR_INVALID, "symbol %u occurs but has frequency 0", i);
+  }
+  memcpy(freqs_out, f16, sizeof f16);
+
+  const uint32_t groups = static_cast<uint32_t>(n_symbols / gst::kGroupSyms);
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = ctx->streams[0];
+  uint8_t *d_sym = nullptr, *d_scratch = nullptr, *d_out = nullptr;
+  uint16_t *d_f = nullptr;
+  uint32_t *d_sizes = nullptr, *d_offsets = nullptr;
+  std::vector<uint32_t> sizes(groups), offsets(groups);
+  size_t total = 0;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_sym), n_symbols);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_scratch), static_cast<size_t>(groups) * gst::kEncGroupCapBytes);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_f), sizeof f16);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_sizes), 4 * static_cast<size_t>(groups));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_offsets), 4 * static_cast<size_t>(groups));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_sym, symbols, n_symbols, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, f16, sizeof f16, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = gst::launch_ans_encode(d_sym, groups, d_f, d_scratch, d_sizes, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sizes.data(), d_sizes, 4 * static_cast<size_t>(groups), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) {
+    // offsets are measured from the start of the stream and include the offset table (codec/entropy.cpp:202-231)
+    size_t cum = 4 * static_cast<size_t>(groups);
+    for (uint32_t g = 0; g < groups; ++g) {
+      cum += (sizes[g] + 3u) & ~3u;
+      offsets[g] = static_cast<uint32_t>(cum);
+    }
+    total = (cum + 3) & ~static_cast<size_t>(3);
+    if (total > stream_cap) {
+      cudaFree(d_sym); cudaFree(d_scratch); cudaFree(d_f); cudaFree(d_sizes); cudaFree(d_offsets);
+      return fail(GST_ERR_INVALID, "stream_out holds %zu bytes, the stream needs %zu", stream_cap, total);
+    }
+    e = cudaMalloc(reinterpret_cast<void **>(&d_out), total);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, total, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, offsets.data(), 4 * static_cast<size_t>(groups), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = gst::launch_ans_encode_gather(d_scratch, d_sizes, d_offsets, groups, d_out, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stream_out, d_out, total, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_sym); cudaFree(d_scratch); cudaFree(d_f); cudaFree(d_sizes); cudaFree(d_offsets);
+  if (d_out) cudaFree(d_out);
+  if (e != cudaSuccess) return fail(GST_ERR_CUDA, "ans encode failed: %s", cudaGetErrorString(e));
+  *stream_bytes = total;
+  return GST_OK;
+}
+
 int gst_ans_rebuild(gst_ans_decoder *d, const uint32_t *F, uint32_t n) {
   if (!d || !F || n == 0 || n > 256) return fail(GST_ERR_INVALID, "need 1..256 symbol counts");
   std::vector<uint32_t> h;

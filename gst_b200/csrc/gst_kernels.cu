@@ -1117,6 +1117,94 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
                                       });
 }
 
+// ---------------------------------------------------------------------------------------
+// rANS ENCODE of one symbol stream, stream-compatible with ByteEncoder::EncodeBytes
+// (codec/entropy.cpp:174-265) = ans::EncodeInterleaved (ans/encode.cpp:224-259) per group of 32 x 256
+// symbols with rANS_Encoder::Encode (ans/encode.cpp:56-69): b = 2^16, k = 2^4, M = 2^11.
+//   lane j of a warp owns stream j = symbols [256 j, 256 j + 256) of the group, in order; per symbol, streams
+//   0..31 in order: while (state >= b k F[s]) emit (state & 0xFFFF), state >>= 16   (at most once: state < 2^31)
+//   state = (state / F[s]) * M + B[s] + state % F[s];  the 32 final states follow the words.
+// The emission order inside a step is the lane order, so a lane's word lands at
+// base + popc(ballot & lanes_below); the decoder reads the same words backwards, higher lanes first.
+// Output: the group's bytes (words then states) at scratch + group * kEncGroupCap, the byte count in
+// sizes[group].  This is fixture tooling: it removes the CPU entropy coder
+// from the path that builds large test sets, and is not part of the decode path.
+constexpr int kEncGroupCap = 2 * kGroupSyms + 4 * kLanes;  // every symbol emits a word + the states
+
+__global__ void __launch_bounds__(256) ans_encode_kernel(const uint8_t *__restrict__ symbols, uint32_t n_groups,
+                                                         const uint16_t *__restrict__ freqs, uint8_t *__restrict__ scratch,
+                                                         uint32_t *__restrict__ sizes) {
+  __shared__ uint32_t s_f[256], s_b[256];
+  __shared__ uint32_t s_warp[8];
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  {  // cumulative frequencies: exclusive scan of the 256 normalised frequencies
+    const uint32_t f = freqs[t];
+    uint32_t inc = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+    s_f[t] = f;
+    s_b[t] = base + inc - f;
+    __syncthreads();
+  }
+  const uint32_t group = blockIdx.x * 8 + warp;
+  if (group >= n_groups) return;
+  const uint8_t *src = symbols + static_cast<size_t>(group) * kGroupSyms + lane * kSymsPerLane;
+  uint16_t *words = reinterpret_cast<uint16_t *>(scratch + static_cast<size_t>(group) * kEncGroupCap);
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t state = kRansL;  // k * M, ans/encode.cpp:47
+  uint32_t n_words = 0;
+#pragma unroll 1
+  for (int i0 = 0; i0 < kSymsPerLane; i0 += 16) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + i0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t sym = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+      const uint32_t F = s_f[sym], B = s_b[sym];
+      // a symbol with F = 0 cannot be coded (the caller's histogram is wrong): treat it as F = 1 so the kernel
+      // terminates; the host checks the histogram before launching
+      const uint32_t Fs = F ? F : 1u;
+      const bool emit = state >= (Fs << 20);  // b k F[s]; F <= 2048 keeps this inside 32 bits
+      const uint32_t mask = __ballot_sync(0xffffffffu, emit);
+      if (emit) {
+        words[n_words + __popc(mask & below)] = static_cast<uint16_t>(state);
+        state >>= 16;
+      }
+      n_words += __popc(mask);
+      const uint32_t q = state / Fs;
+      state = q * kTableSize + B + (state - q * Fs);
+    }
+  }
+  words[n_words + 2 * lane] = static_cast<uint16_t>(state);  // (the states are only 2-byte aligned here)
+  words[n_words + 2 * lane + 1] = static_cast<uint16_t>(state >> 16);
+  if (lane == 0) sizes[group] = 2 * n_words + 4 * kLanes;
+}
+
+// Gathers the groups into the stream ByteEncoder::EncodeBytes emits after its 512-byte frequency block:
+// [u32 end_offset[groups]][group 0][group 1]..., every group padded AT THE FRONT with two zero bytes when
+// its size is not a multiple of four (codec/entropy.cpp:213-228).  offsets[g] = end of group g.
+__global__ void __launch_bounds__(256) ans_encode_gather_kernel(const uint8_t *__restrict__ scratch,
+                                                                const uint32_t *__restrict__ sizes,
+                                                                const uint32_t *__restrict__ offsets, uint32_t n_groups,
+                                                                uint8_t *__restrict__ out) {
+  const uint32_t g = blockIdx.x;
+  const uint32_t size = sizes[g], end = offsets[g];
+  const uint32_t padded = (size + 3u) & ~3u;
+  uint16_t *dst = reinterpret_cast<uint16_t *>(out + end - padded);
+  const uint16_t *src = reinterpret_cast<const uint16_t *>(scratch + static_cast<size_t>(g) * kEncGroupCap);
+  const uint32_t pad16 = (padded - size) / 2;  // 0 or 1 leading zero word
+  if (threadIdx.x == 0 && pad16) dst[0] = 0;
+  for (uint32_t i = threadIdx.x; i < size / 2; i += blockDim.x) dst[pad16 + i] = src[i];
+  if (threadIdx.x == 0) reinterpret_cast<uint32_t *>(out)[g] = end;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -1188,6 +1276,20 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return stamp();
+}
+
+cudaError_t launch_ans_encode(const uint8_t *symbols, uint32_t n_groups, const uint16_t *freqs, uint8_t *scratch,
+                              uint32_t *sizes, cudaStream_t s) {
+  if (n_groups == 0) return cudaSuccess;
+  ans_encode_kernel<<<(n_groups + 7) / 8, 256, 0, s>>>(symbols, n_groups, freqs, scratch, sizes);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ans_encode_gather(const uint8_t *scratch, const uint32_t *sizes, const uint32_t *offsets,
+                                     uint32_t n_groups, uint8_t *out, cudaStream_t s) {
+  if (n_groups == 0) return cudaSuccess;
+  ans_encode_gather_kernel<<<n_groups, 256, 0, s>>>(scratch, sizes, offsets, n_groups, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_ans_decode_plain(const uint32_t *table, const uint8_t *data, uint64_t data_bytes,

@@ -86,6 +86,13 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
 cudaError_t launch_ans_decode_plain(const uint32_t *table, const uint8_t *data,
                                     uint64_t data_bytes, uint32_t n_groups, uint32_t n_lanes,
                                     uint8_t *out, cudaStream_t s);
+// rANS encode of a symbol stream (fixture tooling).  scratch: n_groups * kEncGroupCapBytes,
+// sizes: n_groups u32; the gather writes [u32 end offsets][groups] given offsets[g] = end of group g.
+constexpr size_t kEncGroupCapBytes = 2 * kGroupSyms + 4 * kLanes;
+cudaError_t launch_ans_encode(const uint8_t *symbols, uint32_t n_groups, const uint16_t *freqs, uint8_t *scratch,
+                              uint32_t *sizes, cudaStream_t s);
+cudaError_t launch_ans_encode_gather(const uint8_t *scratch, const uint32_t *sizes, const uint32_t *offsets,
+                                     uint32_t n_groups, uint8_t *out, cudaStream_t s);
 // number of kernels launch_decode_batch enqueues (for bench.py's gpu_launches)
 constexpr int kLaunchesPerBatch = 4;
 

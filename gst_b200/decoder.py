@@ -440,6 +440,32 @@ class FrameStreamer:
             pass
 
 
+def encode_stream(dec, symbols):
+    """ByteEncoder::EncodeBytes (codec/entropy.cpp:174-265) on the GPU: byte symbols (a multiple of
+    8192 of them) -> (512-byte frequency block, stream bytes = [u32 end offsets][rANS groups]).
+    Fixture tooling: it entropy-codes test inputs without the CPU encoder."""
+    s = _as_u8(symbols)
+    freqs = np.empty(256, dtype="<u2")
+    cap = lib().gst_ans_encode_bound(s.size)
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    check(lib().gst_ans_encode_stream(dec.ctx, s.ctypes.data, s.size, freqs.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+    return freqs.view(np.uint8).copy(), out[: n.value].copy()
+
+
+def build_gst(dec, width, height, y_syms, chroma_syms, palette, index_syms):
+    """A .gst container (codec/encoder.cpp:122-144) from raw symbol arrays, entropy-coded on the GPU:
+    y_syms 2N bytes (Y1 || Y2), chroma_syms 4N (Co1 || Cg1 || Co2 || Cg2), palette P bytes (a multiple of
+    8192), index_syms N, with N = (width / 4) * (height / 4)."""
+    n = (width // 4) * (height // 4)
+    arrs = [_as_u8(a) for a in (y_syms, chroma_syms, palette, index_syms)]
+    if [a.size for a in arrs[:2]] + [arrs[3].size] != [2 * n, 4 * n, n] or arrs[2].size % 8192:
+        raise ValueError("symbol arrays do not match the image size")
+    parts = [encode_stream(dec, a) for a in arrs]
+    hdr = np.array([width, height, arrs[2].size] + [p[1].size for p in parts], dtype="<u4").view(np.uint8)
+    return np.concatenate([hdr] + [p[0] for p in parts] + [p[1] for p in parts])
+
+
 class AnsDecoder:
     """ans::ocl::OpenCLDecoder (ans/ans_ocl.h:26-72)."""
 

@@ -193,6 +193,19 @@ int gst_ans_decode(gst_ans_decoder *d, uint32_t lanes, const uint32_t *states,
                    uint8_t *out);
 void gst_ans_destroy(gst_ans_decoder *d);
 
+/* ---- rANS stream ENCODER on the GPU: ByteEncoder::EncodeBytes (codec/entropy.cpp:174-265), i.e.
+ * ans::ocl::NormalizeFrequencies of the byte histogram + ans::EncodeInterleaved (ans/encode.cpp:224-259,
+ * rANS_Encoder::Encode ans/encode.cpp:56-69) per group of 32 x 256 symbols.  Fixture tooling (it lets
+ * large test sets be entropy-coded without the CPU encoder); not on the decode path.
+ *   symbols, n_symbols : host bytes, n_symbols a multiple of 8192
+ *   freqs_out          : 256 x u16, the normalised frequencies = the 512-byte block of the .gst file
+ *   stream_out         : [u32 end_offset[groups]][groups...] padded to 4 bytes, exactly the bytes
+ *                        EncodeBytes emits after the frequency block; *stream_bytes receives the size.
+ *                        stream_cap >= gst_ans_encode_bound(n_symbols) always suffices. */
+size_t gst_ans_encode_bound(size_t n_symbols);
+int gst_ans_encode_stream(gst_ctx *ctx, const uint8_t *symbols, size_t n_symbols, uint16_t *freqs_out,
+                          uint8_t *stream_out, size_t stream_cap, size_t *stream_bytes);
+
 /* stage 1 on caller buffers: n tables of 256 x u16 frequencies (512 B each, as stored in
  * the .gst file) -> n x 2048 packed u32 entries  sym | freq << 8 | (slot - cum) << 20. */
 int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t n_tables,

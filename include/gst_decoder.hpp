@@ -327,6 +327,19 @@ class CUDADecoder {
 };
 typedef CUDADecoder OpenCLDecoder;  // drop-in name for code written against ans/ans_ocl.h
 
+// ByteEncoder::EncodeBytes::Run (codec/entropy.cpp:174-265) on the GPU: the 512-byte frequency block followed
+// by [u32 end offsets][rANS groups], byte for byte what the reference's CPU encoder returns for the same
+// symbols (a multiple of 32 * 256 of them).  Fixture tooling; the decode path does not use it.
+inline std::vector<uint8_t> EncodeBytes(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, const std::vector<uint8_t> &symbols) {
+  std::vector<uint8_t> out(512 + gst_ans_encode_bound(symbols.size()));
+  size_t n = 0;
+  if (gst_ans_encode_stream(gpu_ctx->Handle(), symbols.data(), symbols.size(), reinterpret_cast<uint16_t *>(out.data()),
+                            out.data() + 512, out.size() - 512, &n) != GST_OK)
+    throw std::runtime_error(gst_last_error());
+  out.resize(512 + n);
+  return out;
+}
+
 }  // namespace ocl
 }  // namespace ans
 
