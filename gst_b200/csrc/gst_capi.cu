@@ -156,6 +156,7 @@ int layout_batch(const gst_header *hdrs, uint32_t n, BatchLayout *L) {
   // the device-side offset table is cl_uint (codec/decoder.cpp:133-149)
   if (in_total > 0xFFFFFFFFull || out_total > 0xFFFFFFFFull)
     return fail(GST_ERR_INVALID, "batch of %u images overflows the 32-bit stream offsets; split it into pages", n);
+  if (n > 65535u) return fail(GST_ERR_INVALID, "batch of %u images: one call takes at most 65535; split it into pages", n);
   L->n_blocks = static_cast<uint32_t>(N);
   L->groups_per_plane = static_cast<uint32_t>(N / gst::kGroupSyms);
   L->max_palette = max_pal;
@@ -225,7 +226,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.palette_cap = L.palette_total;
   p.idx_s = scratch + L.idx_off;
   p.idx16 = L.idx16 ? 1u : 0u;
-  p.idx_total = reinterpret_cast<int32_t *>(scratch + L.total_off);
+  p.idx_carry = reinterpret_cast<int32_t *>(scratch + L.total_off);
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
   p.tap_symbols = static_cast<uint8_t *>(taps.symbols);

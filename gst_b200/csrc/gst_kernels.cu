@@ -8,7 +8,6 @@
 //                            palette, and for the index stream stage 3 (codec/decode_indices.cl:6-84,
 //                            host loop codec/decoder.cpp:311-393) is fused behind the rANS warp as a
 //                            group-local suffix sum
-//   index_carry_kernel       the cross-group part of stage 3 (exclusive scan of group totals)
 //   wavelet_assemble_kernel  stage 4 (codec/inverse_wavelet.cl:69-192) and stage 5
 //                            (codec/assemble.cl:64-129): one warp per 32x32 tile, all six planes;
 //                            the wavelet planes never leave shared memory
@@ -263,8 +262,12 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
 // symbol x with cum[x] <= slot < cum[x+1].  The reference scans then binary-searches per slot;
 // here every symbol with a non-zero frequency drops its id at slot cum[x] and a max-scan
 // spreads it -- the result is determined by the frequencies alone, so it is identical.
+// The kernel also zeroes `zero_words` 32-bit words at `zero` (the index-carry accumulators of the batch,
+// which rans_streams_kernel adds to): it is the first launch of a call, so no separate memset is needed.
 __global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__restrict__ freqs,
-                                                           uint32_t *__restrict__ tables) {
+                                                           uint32_t *__restrict__ tables, uint32_t *__restrict__ zero,
+                                                           uint32_t zero_words) {
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < zero_words; i += gridDim.x * 256) zero[i] = 0u;
   __shared__ uint32_t s_freq[256];
   __shared__ uint32_t s_cum[256];
   __shared__ uint32_t s_sym[kTableSize];
@@ -373,7 +376,8 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 //       Stage 3 (codec/decode_indices.cl:24, idx[i] = sum_{j<=i} d[j]) is fused behind the
 //       decoder: symbols arrive last-to-first, so the lane writes S[i] = sum of the deltas AFTER
 //       i inside its run, and idx[i] = run_end[run] - S[i], where run_end is the inclusive
-//       prefix at the end of the run (finished by index_carry_kernel).  S is stored mod 2^16
+//       prefix at the end of the run (group-local here, the carry of the earlier groups is added by
+//       wavelet_assemble_kernel).  S is stored mod 2^16
 //       when every palette of the batch has <= 65536 entries (idx < 2^16 then makes the 16-bit
 //       difference exact), else as 32 bits, in the same transposed order as sym_t:
 //       [group][k][lane][16 values].
@@ -498,7 +502,9 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
                                    }
                                  }
                                });
-  // group-local inclusive prefix at the end of every run, and the group total
+  // group-local inclusive prefix at the end of every run; the group total goes into the carry of every later
+  // group of the image (the cross-group part of stage 3, codec/decode_indices.cl:66-84: integer atomics,
+  // so the order of arrival does not matter; build_tables_kernel zeroed the accumulators)
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     uint32_t inc = sum[c];
@@ -508,7 +514,9 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
       if (lane >= d) inc += n;
     }
     p.run_end[static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + (group + c) * kLanes + lane] = static_cast<int32_t>(inc);
-    if (lane == 31) p.idx_total[static_cast<size_t>(b) * p.groups_per_plane + group + c] = static_cast<int32_t>(inc);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    int32_t *carry = p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane;
+    for (uint32_t g = group + c + 1 + lane; g < p.groups_per_plane; g += 32) atomicAdd(carry + g, static_cast<int32_t>(total));
   }
 }
 
@@ -556,41 +564,6 @@ __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const 
     rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring);
   else
     rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring);
-}
-
-// The cross-group part of stage 3 (what the collect_indices passes of
-// codec/decode_indices.cl:66-84 do): exclusive scan of the group totals of one image, added to
-// the group-local run ends.  One CTA per image.
-__global__ void __launch_bounds__(256) index_carry_kernel(const BatchParams p) {
-  __shared__ uint32_t s_warp[8];
-  __shared__ uint32_t s_base;
-  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int32_t *tot = p.idx_total + static_cast<size_t>(blockIdx.x) * p.groups_per_plane;
-  int32_t *run_end = p.run_end + static_cast<size_t>(blockIdx.x) * (p.n_blocks / kSymsPerLane);
-  if (t == 0) s_base = 0;
-  __syncthreads();
-  for (uint32_t i0 = 0; i0 < p.groups_per_plane; i0 += 256) {
-    const uint32_t i = i0 + t;
-    const uint32_t v = i < p.groups_per_plane ? static_cast<uint32_t>(tot[i]) : 0u;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += n;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t base = s_base;
-    for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
-    const uint32_t carry = base + inc - v;  // exclusive
-    if (i < p.groups_per_plane) {
-      // the 32 runs of group i
-      for (uint32_t l = 0; l < kLanes; ++l) run_end[i * kLanes + l] += static_cast<int32_t>(carry);
-    }
-    __syncthreads();
-    if (t == 255) s_base = base + inc;
-    __syncthreads();
-  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -851,11 +824,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
-  const uint32_t tiles_per_image = p.n_blocks / kTileSyms;
-  const uint32_t gt_tile = blockIdx.x * kWaWarps + warp;  // tile index over the whole batch
-  const uint32_t b = gt_tile / tiles_per_image;
-  if (b >= p.n_images) return;
-  const uint32_t tile = gt_tile % tiles_per_image;
+  // grid = (tile pairs of an image, images): no division by the tiles per image
+  const uint32_t b = blockIdx.y;
+  const uint32_t tile = blockIdx.x * kWaWarps + warp;
+  if (tile >= p.n_blocks / kTileSyms) return;
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
 
@@ -887,11 +859,13 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
   const int32_t *run_end = p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane);
   const bool idx16 = p.idx16 != 0;
+  // index prefix at the end of a run = its group-local prefix + the carry of the earlier groups (both from rans_streams_kernel)
+  const int32_t *carry = p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane;
   // first block of this lane in slab k (rows 4k..4k+3 of the tile)
   const uint32_t gidx0 = (ty * kTile + (lane >> 3)) * p.blocks_x + tx * kTile + 4 * (lane & 7);
   const uint32_t slab_stride = 4 * p.blocks_x;
   // S of 4 blocks (raw) + the run end; words = the 4 palette words
-  struct Sfx { uint4 raw; uint32_t re; };
+  struct Sfx { uint4 raw; uint32_t re, cy; };
   // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
   auto sfx_ptr = [&](uint32_t gidx) -> const uint8_t * {
     const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
@@ -906,6 +880,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
       r.raw = __ldg(reinterpret_cast<const uint4 *>(sp));
     }
     r.re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
+    r.cy = static_cast<uint32_t>(__ldg(carry + gidx / kGroupSyms));
     return r;
   };
   auto load_sfx = [&](uint32_t gidx) -> Sfx { return load_sfx_at(sfx_ptr(gidx), gidx); };
@@ -919,10 +894,11 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     } else {
       sfx[0] = sf.raw.x; sfx[1] = sf.raw.y; sfx[2] = sf.raw.z; sfx[3] = sf.raw.w;
     }
+    const uint32_t re = sf.re + sf.cy;
     uint32_t idx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      idx[j] = sf.re - sfx[j];
+      idx[j] = re - sfx[j];
       if (idx16) idx[j] &= 0xFFFFu;
       word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
     }
@@ -1210,9 +1186,9 @@ __global__ void __launch_bounds__(256) ans_encode_gather_kernel(const uint8_t *_
 // ---------------------------------------------------------------------------------------
 // launchers
 cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,
-                                cudaStream_t s) {
+                                cudaStream_t s, uint32_t *zero, uint32_t zero_words) {
   if (n_tables == 0) return cudaSuccess;
-  build_tables_kernel<<<n_tables, 256, 0, s>>>(freqs, tables);
+  build_tables_kernel<<<n_tables, 256, 0, s>>>(freqs, tables, zero, zero_words);
   return cudaGetLastError();
 }
 
@@ -1240,7 +1216,8 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   auto stamp = [&]() { return marks ? cudaEventRecord(marks[mark++], s) : cudaSuccess; };
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 1: 4 tables per image, straight from the freq region of the compressed buffer
-  e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s);
+  e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s, reinterpret_cast<uint32_t *>(p.idx_carry),
+                          p.n_images * p.groups_per_plane);
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
@@ -1258,13 +1235,9 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
-  index_carry_kernel<<<p.n_images, 256, 0, s>>>(p);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  if ((e = stamp()) != cudaSuccess) return e;
-  // stages 4 + 5: one warp per tile
-  const uint64_t tiles = static_cast<uint64_t>(p.n_images) * (p.n_blocks / kTileSyms);
-  const uint32_t grid = static_cast<uint32_t>((tiles + kWaWarps - 1) / kWaWarps);
+  // stages 4 + 5 (and the cross-group carry of stage 3): one warp per tile
+  if (p.n_images > 65535u) return cudaErrorInvalidValue;  // grid.y; gst_capi.cu pages larger batches
+  const dim3 grid((p.n_blocks / kTileSyms + kWaWarps - 1) / kWaWarps, p.n_images);
   if (rgb_mode && taps)
     wavelet_assemble_kernel<1, true><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
   else if (rgb_mode)

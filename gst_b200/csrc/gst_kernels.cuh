@@ -4,7 +4,7 @@
 // Reference stages (citations relative to the reference tree):
 //   1. ans/build_table.cl:12-83           -> build_tables_kernel
 //   2. ans/ans_decode.cl:25-143           -> rans_decode_group() inside every decode kernel
-//   3. codec/decode_indices.cl:6-84       -> rans_streams_kernel (scan fused behind the rANS warp) + index_carry_kernel
+//   3. codec/decode_indices.cl:6-84       -> rans_streams_kernel (scan fused behind the rANS warp) + the carry in wavelet_assemble_kernel
 //   4. codec/inverse_wavelet.cl:69-192    -> wavelet_assemble_kernel
 //   5. codec/assemble.cl:64-129           -> wavelet_assemble_kernel
 #pragma once
@@ -66,8 +66,8 @@ struct BatchParams {
   uint64_t palette_cap;      // bytes available in `palette`
   void *idx_s;               // [B][N] u16 or u32, transposed like sym_t: sum of the index deltas after block i in its 256-block run
   uint32_t idx16;            // 1: idx_s holds u16 (every palette <= 65536 entries), 0: u32
-  int32_t *run_end;          // [B][N/256] inclusive index prefix at the end of every run
-  int32_t *idx_total;        // [B][N/8192] sum of every index group
+  int32_t *run_end;          // [B][N/256] group-local inclusive index prefix at the end of every run
+  int32_t *idx_carry;        // [B][N/8192] sum of the index groups BEFORE each group (accumulated with atomics)
   // outputs
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
   // optional taps for the stage parity tests (NULL in production)
@@ -78,7 +78,7 @@ struct BatchParams {
 
 // launch helpers (gst_kernels.cu)
 cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,
-                                cudaStream_t s);
+                                cudaStream_t s, uint32_t *zero = nullptr, uint32_t zero_words = 0);
 // max_palette_bytes = max over the batch of GenTCHeader::palette_bytes (sizes the grid)
 // marks: NULL, or kLaunchesPerBatch + 1 events recorded around every kernel (profiling)
 cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,
@@ -94,6 +94,6 @@ cudaError_t launch_ans_encode(const uint8_t *symbols, uint32_t n_groups, const u
 cudaError_t launch_ans_encode_gather(const uint8_t *scratch, const uint32_t *sizes, const uint32_t *offsets,
                                      uint32_t n_groups, uint8_t *out, cudaStream_t s);
 // number of kernels launch_decode_batch enqueues (for bench.py's gpu_launches)
-constexpr int kLaunchesPerBatch = 4;
+constexpr int kLaunchesPerBatch = 3;
 
 }  // namespace gst

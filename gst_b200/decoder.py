@@ -274,7 +274,7 @@ class Decoder:
             self.sync(s)
 
     # -- profiling -----------------------------------------------------------------------
-    KERNEL_NAMES = ("build_tables", "rans_streams", "index_carry", "wavelet_assemble")
+    KERNEL_NAMES = ("build_tables", "rans_streams", "wavelet_assemble")
 
     def profile(self, on=True):
         check(lib().gst_profile_enable(self.ctx, 1 if on else 0))

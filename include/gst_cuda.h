@@ -207,12 +207,13 @@ int gst_ans_encode_stream(gst_ctx *ctx, const uint8_t *symbols, size_t n_symbols
                           uint8_t *stream_out, size_t stream_cap, size_t *stream_bytes);
 
 /* stage 1 on caller buffers: n tables of 256 x u16 frequencies (512 B each, as stored in
- * the .gst file) -> n x 2048 packed u32 entries  sym | freq << 8 | (slot - cum) << 20. */
+ * the .gst file) -> n x 2048 packed u32 entries
+ * freq | sym << 11 | bias' << 19 (gst_kernels.cuh). */
 int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t n_tables,
                      void *tables_dev);
 
 /* number of kernel launches one gst_load_*_batch call enqueues, in launch order:
- * build_tables, side_streams (palette + index rANS), index_carry, fused_planes */
+ * build_tables, rans_streams (all four streams + the group-local index scan), wavelet_assemble */
 int gst_launches_per_batch(void);
 
 /* Per-kernel device timing for the benchmark's roofline line (no reference equivalent; the
