@@ -3,14 +3,16 @@
 // Kernel inventory (reference stage it replaces, citations relative to the reference tree):
 //   build_tables_kernel      stage 1  ans/build_table.cl:12-83
 //   rans_streams_kernel      stage 2  ans/ans_decode.cl:25-143 for all four streams of every image,
-//                            one warp per 32-stream group at full occupancy.  Plane symbols go to
-//                            an L2-friendly transposed scratch, palette symbols to the compact
-//                            palette, and for the index stream stage 3 (codec/decode_indices.cl:6-84,
-//                            host loop codec/decoder.cpp:311-393) is fused behind the rANS warp as a
-//                            group-local suffix sum
+//                            one warp per two 32-stream groups.  Plane symbols go to a transposed,
+//                            plane-pair-interleaved scratch, palette symbols to the compact palette,
+//                            and for the index stream stage 3 (codec/decode_indices.cl:6-84, host loop
+//                            codec/decoder.cpp:311-393) is fused behind the rANS warp as a group-local
+//                            suffix sum plus an atomic carry into the later groups
 //   wavelet_assemble_kernel  stage 4 (codec/inverse_wavelet.cl:69-192) and stage 5
-//                            (codec/assemble.cl:64-129): one warp per 32x32 tile, all six planes;
-//                            the wavelet planes never leave shared memory
+//                            (codec/assemble.cl:64-129): one warp per 32x32 tile, all six planes as
+//                            three packed plane pairs; the wavelet planes never leave shared memory
+//   ans_encode_kernel,       the entropy stage of the ENCODER (codec/entropy.cpp:174-265), fixture tooling
+//   ans_encode_gather_kernel
 //   ans_decode_plain_kernel  the standalone `ans_decode` entry (ans/ans_decode.cl:76-95),
 //                            1..32 interleaved lanes, used by the OpenCLDecoder-style API
 //
@@ -356,19 +358,21 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 }
 
 // ---------------------------------------------------------------------------------------
-// Stage 2 for every stream of every image.  One warp per rANS group, 8 warps per CTA, all warps
-// of a CTA on the same stream of the same image (one 8 KiB table in shared memory); 16 KiB of
-// shared memory and <= 32 registers per thread, so an SM holds 64 warps = 64 independent rANS
-// chains -- the decode loop is a chain of dependent shared-memory lookups (~200 cycles per
-// symbol), and only this many chains keep the issue slots busy.
+// Stage 2 for every stream of every image.  One warp per TWO rANS groups (two interleaved chains), 8
+// warps per CTA, all warps of a CTA on the same stream of the same image (one 8 KiB table in shared
+// memory); 42 KiB of shared memory and 48 registers per thread, so an SM holds 5 CTAs = 40 warps = 80
+// independent rANS chains.  The decode loop is a chain of dependent shared-memory lookups (~150 cycles
+// per symbol); with this many chains the kernel is bound by the mix of ALU pipe, issue slots and
+// shared-memory wavefronts (each 65-72 % busy, profiles/), not by that latency.
 //
 //   Y / chroma groups: the symbols are the wavelet coefficients of the six endpoint planes
 //       (Y = Y1 || Y2, chroma = Co1 || Cg1 || Co2 || Cg2, codec/encoder.cpp:87,93-95), one group =
-//       8 tiles of one plane.  They go to the transposed scratch sym_t: image b, plane-group
-//       pg = plane * groups_per_plane + g holds [k = 0..15][lane = 0..31][16 B], where the 16
-//       bytes are positions 16k..16k+15 of the lane's run.  One warp store is 512 contiguous
-//       bytes (the reference layout would be 32 pieces 256 B apart); wavelet_assemble_kernel
-//       reads 16-byte pieces, which is all it needs.
+//       8 tiles of one plane.  A warp takes the same group of the two planes of a pair (Y1|Y2, Co1|Co2,
+//       Cg1|Cg2) as its two chains and writes them byte-interleaved to the transposed scratch sym_t:
+//       image b, pair-group pg = pair * groups_per_plane + g holds [k = 0..15][lane = 0..31][32 B], the
+//       32 bytes being positions 16k..16k+15 of the lane's run as (plane A, plane B) pairs.  One warp
+//       store is 1 KiB contiguous (the reference layout would be 32 pieces 256 B apart);
+//       wavelet_assemble_kernel reads 16-byte pieces, which is all it needs.
 //   palette groups: symbols go straight to the compact palette scratch (they are the u32 DXT
 //       index words, codec/encoder.cpp:100-108)
 //   index groups: symbols are (delta + 128) per DXT block in raster order
