@@ -387,8 +387,13 @@ def main():
         per_image_s = 0.11 * (width * height) / (2048.0 * 2048.0)  # survey probe, one core
         sample = args.cpu_sample or int(max(1, min(images, 15.0 / max(per_image_s, 1e-4))))
         dt, kind = cpu_decode_rate(files, sample, threads)
+        # the same decode on ONE host thread as well (a few images)
+        one = int(max(1, min(sample, 3.0 / max(per_image_s, 1e-4))))
+        dt1, _ = cpu_decode_rate(files, one, 1)
         cpu = {"value": float(width) * height * sample / dt / 1e9, "unit": "GTexel/s", "cores": threads, "kind": kind,
-               "sample": f"{sample} images of {width}x{height} ({distinct} distinct), one image per task, {dt:.2f} s wall"}
+               "sample": f"{sample} images of {width}x{height} ({distinct} distinct), one image per task, {dt:.2f} s wall",
+               "single_thread": {"value": float(width) * height * one / dt1 / 1e9, "unit": "GTexel/s", "cores": 1,
+                                 "sample": f"{one} images, {dt1:.2f} s wall"}}
 
     if rank == 0:
         peaks = {}
