@@ -52,6 +52,13 @@ BENCH_KERNEL(k_mix_imad_hadd2, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(
 BENCH_KERNEL(k_mix_lop_shfl, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("shfl.sync.idx.b32 %0, %0, 0, 0x1f, 0xffffffff;" : "+r"(v[j]));)
 BENCH_KERNEL(k_mix3, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c)); { float f = __uint_as_float(v[j]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); v[j] = __float_as_uint(f); })
 BENCH_KERNEL(k_lea, asm volatile("{ .reg .u32 t; shl.b32 t, %0, 3; add.u32 %0, t, %1; }" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_viadd16x2, asm volatile("add.s16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_vimnmx16x2, asm volatile("max.s16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_lop_viadd16x2, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("add.s16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_imad_viadd16x2, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("add.s16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_lop_vimnmx16x2, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("max.s16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_iadd3, asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t; }" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_imax, asm volatile("max.s32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
 BENCH_KERNEL(k_sar_fix, { int x = (int)v[j]; x = x / 4; v[j] = (uint32_t)x + k; })
 
 __global__ void __launch_bounds__(1024) k_lds(uint32_t *out, uint32_t seed) {
@@ -92,7 +99,9 @@ int main() {
       {"DP2A", k_dp2a, 1}, {"LOP3+DP4A alternating", k_mix_lop_dp4a, 2}, {"IMAD+DP4A alternating", k_mix_imad_dp4a, 2},
       {"LOP3+2xIADD", k_mix_lop_iadd3, 3}, {"LOP3+HADD2 alternating", k_mix_lop_hadd2, 2},
       {"IMAD+HADD2 alternating", k_mix_imad_hadd2, 2}, {"LOP3+SHFL alternating", k_mix_lop_shfl, 2},
-      {"LOP3+IMAD+FFMA", k_mix3, 3}, {"SHL+ADD (LEA?)", k_lea, 1}, {"x/4 signed (+IADD)", k_sar_fix, 1}};
+      {"LOP3+IMAD+FFMA", k_mix3, 3}, {"VIADD.16x2 (add.s16x2)", k_viadd16x2, 1}, {"VIMNMX.16x2 (max.s16x2)", k_vimnmx16x2, 1},
+      {"LOP3+VIADD.16x2 alternating", k_mix_lop_viadd16x2, 2}, {"IMAD+VIADD.16x2 alternating", k_mix_imad_viadd16x2, 2},
+      {"LOP3+VIMNMX.16x2 alternating", k_mix_lop_vimnmx16x2, 2}, {"VIMNMX (max.s32)", k_imax, 1}, {"SHL+ADD (LEA?)", k_lea, 1}, {"x/4 signed (+IADD)", k_sar_fix, 1}};
   printf("device %s, %d SMs, clock attr %d kHz\n", prop.name, sms, khz);
   printf("%-34s %12s %16s\n", "instruction", "ms", "thread-ops/clk/SM");
   for (auto &e : ks) {
