@@ -823,7 +823,8 @@ __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t 
 constexpr int kWaWarps = 2;
 constexpr int kWaSmem = kWaWarps * kWarpWork;  // 24576
 
-template <int RGB, bool TAP>
+// IDX16: the index suffix sums are u16 (every palette of the batch has <= 65536 entries), else u32.
+template <int RGB, bool TAP, bool IDX16>
 __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(const BatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -861,51 +862,51 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
 
   // ---- assembly inputs of slab 0 start their trip now ---------------------------------
   const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
-  const int32_t *run_end = p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane);
-  const bool idx16 = p.idx16 != 0;
-  // index prefix at the end of a run = its group-local prefix + the carry of the earlier groups (both from rans_streams_kernel)
-  const int32_t *carry = p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane;
+  // index prefix at the end of a run = its group-local prefix + the carry of the earlier groups (both from
+  // rans_streams_kernel).  The 32 blocks of a tile row lie in one 256-block run, so lane l fetches the run end
+  // of tile row l once, now, and the slabs pick theirs up with a shuffle.
+  uint32_t re_row;
+  {
+    const uint32_t g_row = (ty * kTile + lane) * p.blocks_x + tx * kTile;
+    re_row = static_cast<uint32_t>(__ldg(p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + g_row / kSymsPerLane)) +
+             static_cast<uint32_t>(__ldg(p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane + g_row / kGroupSyms));
+  }
   // first block of this lane in slab k (rows 4k..4k+3 of the tile)
   const uint32_t gidx0 = (ty * kTile + (lane >> 3)) * p.blocks_x + tx * kTile + 4 * (lane & 7);
   const uint32_t slab_stride = 4 * p.blocks_x;
-  // S of 4 blocks (raw) + the run end; words = the 4 palette words
-  struct Sfx { uint4 raw; uint32_t re, cy; };
+  // S of 4 blocks: 4 x u16 in raw.x/.y, or 4 x u32
+  struct Sfx { uint4 raw; };
   // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
   auto sfx_ptr = [&](uint32_t gidx) -> const uint8_t * {
     const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
-    return reinterpret_cast<const uint8_t *>(p.idx_s) + (idx16 ? 2 * e : 4 * e);
+    return reinterpret_cast<const uint8_t *>(p.idx_s) + (IDX16 ? 2 * e : 4 * e);
   };
-  auto load_sfx_at = [&](const uint8_t *sp, uint32_t gidx) -> Sfx {
+  auto load_sfx_at = [&](const uint8_t *sp) -> Sfx {
     Sfx r;
-    if (idx16) {
+    if (IDX16) {
       const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(sp));
       r.raw = make_uint4(sv.x, sv.y, 0u, 0u);
     } else {
       r.raw = __ldg(reinterpret_cast<const uint4 *>(sp));
     }
-    r.re = static_cast<uint32_t>(__ldg(run_end + gidx / kSymsPerLane));
-    r.cy = static_cast<uint32_t>(__ldg(carry + gidx / kGroupSyms));
     return r;
   };
-  auto load_sfx = [&](uint32_t gidx) -> Sfx { return load_sfx_at(sfx_ptr(gidx), gidx); };
+  auto load_sfx = [&](uint32_t gidx) -> Sfx { return load_sfx_at(sfx_ptr(gidx)); };
   // the suffix sums come from DRAM (the rANS kernel wrote them): pull them into L1 two slabs before
   // they are loaded, so that the load -> index -> palette gather chain of a slab starts on time
   auto prefetch_sfx = [&](const uint8_t *sp) { asm volatile("prefetch.global.L1 [%0];" ::"l"(sp)); };
-  auto load_words = [&](const Sfx &sf, uint32_t gidx, uint32_t (&word)[4]) {
-    uint32_t sfx[4];
-    if (idx16) {
-      sfx[0] = sf.raw.x & 0xFFFFu; sfx[1] = sf.raw.x >> 16; sfx[2] = sf.raw.y & 0xFFFFu; sfx[3] = sf.raw.y >> 16;
-    } else {
-      sfx[0] = sf.raw.x; sfx[1] = sf.raw.y; sfx[2] = sf.raw.z; sfx[3] = sf.raw.w;
-    }
-    const uint32_t re = sf.re + sf.cy;
+  // k = slab of these suffix sums
+  auto load_words = [&](const Sfx &sf, uint32_t k, uint32_t gidx, uint32_t (&word)[4]) {
+    const uint32_t re = __shfl_sync(0xffffffffu, re_row, 4 * k + (lane >> 3));
     uint32_t idx[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      idx[j] = re - sfx[j];
-      if (idx16) idx[j] &= 0xFFFFu;
-      word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
+    if (IDX16) {  // idx = (re - S) mod 2^16; the other half of the word only reaches the bits that are masked off
+      idx[0] = (re - sf.raw.x) & 0xFFFFu; idx[1] = (re - (sf.raw.x >> 16)) & 0xFFFFu;
+      idx[2] = (re - sf.raw.y) & 0xFFFFu; idx[3] = (re - (sf.raw.y >> 16)) & 0xFFFFu;
+    } else {
+      idx[0] = re - sf.raw.x; idx[1] = re - sf.raw.y; idx[2] = re - sf.raw.z; idx[3] = re - sf.raw.w;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
     if (TAP && p.tap_indices)
       *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
   };
@@ -934,9 +935,9 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     n_entries = palette_bytes / 4;
     pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
     pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? pal_off : 0));
-    load_words(sa, gidx0, word_nx);
+    load_words(sa, 0, gidx0, word_nx);
     sa = sb;
-    sb = load_sfx_at(pf_a, gidx0 + 2 * slab_stride);
+    sb = load_sfx_at(pf_a);
     pf_a = pf_b;
     pf_b = sfx_ptr(gidx0 + 4 * slab_stride);
     prefetch_sfx(pf_b);
@@ -985,9 +986,9 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   for (uint32_t k = 0; k < 8; ++k) {
     const uint32_t gidx = gidx0 + k * slab_stride;
     const uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
-    if (k + 1 < 8) load_words(sa, gidx + slab_stride, word_nx);  // its S / run end were loaded two slabs ago
+    if (k + 1 < 8) load_words(sa, k + 1, gidx + slab_stride, word_nx);  // its S was loaded two slabs ago
     sa = sb;
-    if (k + 3 < 8) sb = load_sfx_at(pf_a, gidx + 3 * slab_stride);
+    if (k + 3 < 8) sb = load_sfx_at(pf_a);
     pf_a = pf_b;
     if (k + 5 < 8) {
       pf_b = sfx_ptr(gidx + 5 * slab_stride);
@@ -1199,8 +1200,9 @@ cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_
 static cudaError_t ensure_attrs() {
   static cudaError_t once = []() {
     cudaError_t e = cudaSuccess;
-    for (auto *k : {wavelet_assemble_kernel<0, false>, wavelet_assemble_kernel<1, false>, wavelet_assemble_kernel<0, true>,
-                    wavelet_assemble_kernel<1, true>}) {
+    for (auto *k : {wavelet_assemble_kernel<0, false, true>, wavelet_assemble_kernel<1, false, true>, wavelet_assemble_kernel<0, true, true>,
+                    wavelet_assemble_kernel<1, true, true>, wavelet_assemble_kernel<0, false, false>, wavelet_assemble_kernel<1, false, false>,
+                    wavelet_assemble_kernel<0, true, false>, wavelet_assemble_kernel<1, true, false>}) {
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem)) != cudaSuccess) return e;
     }
     for (auto *k : {rans_streams_kernel<false>, rans_streams_kernel<true>}) {
@@ -1242,14 +1244,18 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   // stages 4 + 5 (and the cross-group carry of stage 3): one warp per tile
   if (p.n_images > 65535u) return cudaErrorInvalidValue;  // grid.y; gst_capi.cu pages larger batches
   const dim3 grid((p.n_blocks / kTileSyms + kWaWarps - 1) / kWaWarps, p.n_images);
-  if (rgb_mode && taps)
-    wavelet_assemble_kernel<1, true><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
-  else if (rgb_mode)
-    wavelet_assemble_kernel<1, false><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
-  else if (taps)
-    wavelet_assemble_kernel<0, true><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
-  else
-    wavelet_assemble_kernel<0, false><<<grid, kWaWarps * 32, kWaSmem, s>>>(p);
+  auto launch = [&](auto kern) { kern<<<grid, kWaWarps * 32, kWaSmem, s>>>(p); };
+  const int variant = (rgb_mode ? 1 : 0) | (taps ? 2 : 0) | (p.idx16 ? 4 : 0);
+  switch (variant) {
+    case 0: launch(wavelet_assemble_kernel<0, false, false>); break;
+    case 1: launch(wavelet_assemble_kernel<1, false, false>); break;
+    case 2: launch(wavelet_assemble_kernel<0, true, false>); break;
+    case 3: launch(wavelet_assemble_kernel<1, true, false>); break;
+    case 4: launch(wavelet_assemble_kernel<0, false, true>); break;
+    case 5: launch(wavelet_assemble_kernel<1, false, true>); break;
+    case 6: launch(wavelet_assemble_kernel<0, true, true>); break;
+    default: launch(wavelet_assemble_kernel<1, true, true>); break;
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return stamp();
