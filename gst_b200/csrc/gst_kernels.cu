@@ -878,8 +878,10 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   struct Sfx { uint4 raw; };
   // transposed S: [group][k = pos / 16][run][pos % 16], pos = position inside the 256-block run
   auto sfx_ptr = [&](uint32_t gidx) -> const uint8_t * {
-    const size_t e = img_block0 + (gidx & ~8191u) + ((gidx & 255u) >> 4) * 512 + ((gidx & 8191u) >> 8) * 16 + (gidx & 15u);
-    return reinterpret_cast<const uint8_t *>(p.idx_s) + (IDX16 ? 2 * e : 4 * e);
+    // = (gidx & ~8191) + ((gidx & 255) >> 4) * 512 + ((gidx & 8191) >> 8) * 16 + (gidx & 15), with h = gidx >> 4
+    const uint32_t h = gidx >> 4;
+    const uint32_t e32 = (gidx & ~8191u) + ((h & 15u) << 9) + (h & 0x1F0u) + (gidx & 15u);
+    return reinterpret_cast<const uint8_t *>(p.idx_s) + (IDX16 ? 2 : 4) * (img_block0 + e32);
   };
   auto load_sfx_at = [&](const uint8_t *sp) -> Sfx {
     Sfx r;
