@@ -99,23 +99,28 @@ __device__ __forceinline__ uint32_t sext_byte_pair(uint32_t w) {
 // a group ends with its n_lanes 32-bit states, preceded by the shared 16-bit renorm words,
 // which are consumed backwards, higher lanes first (ans/ans_decode.cl:30-32,51-65).
 //
-// The renorm words are staged through a per-warp, 2 KiB-aligned shared-memory ring filled with
-// cp.async in 512-byte, 512-byte-aligned chunks (one 16-byte copy per lane; group ranges are
-// only 4-byte aligned, so the windows are aligned down in absolute address space and the ring
-// is indexed by the low address bits).  A checkpoint every 8 symbols (which consume at most
-// 8*32*2 = 512 B) tops the ring up whenever fewer than 1536 B are staged and then waits until at
-// most the two newest cp.async groups are pending: a chunk has two checkpoint intervals to
-// land, and because at least 1024 B are staged at every checkpoint, the 512 B the next eight
-// symbols can touch are always complete.
+// The renorm words are staged through a per-chain shared-memory ring of three 512-byte slots filled with
+// cp.async, one 512-byte-aligned chunk of the stream per slot (one 16-byte copy per lane; group ranges are
+// only 4-byte aligned, so the windows are aligned down in absolute address space).  Going down the stream
+// by 512 bytes goes down one slot, from slot 0 back to slot 2.  A checkpoint every 8 symbols (which
+// consume at most 8*32*2 = 512 B) stages the next chunk whenever fewer than 1024 B are staged and then
+// waits until only that newest copy is pending: at least 512 complete bytes lie below the next word, which
+// is all the next eight symbols can touch, and a chunk has a whole interval (thousands of cycles) to land.
+//
+// Inside an interval the word address is NOT wrapped: below slot 0 sit 512 bytes that mirror slot 2
+// (whatever is staged into slot 2 is staged there too), so an address that runs off the bottom of the
+// ring during the eight symbols still finds its word, and the decode step needs no instruction to fold
+// the address back -- the checkpoint does it (+1536 when it has left the ring).
 //
 // Per symbol and lane (ans/ans_decode.cl:38-65):
 //   e = table[state & 2047];  state = (state >> 11) * e.freq + slot - e.cum   (as umulhi, see gst_kernels.cuh)
 //   lanes whose state fell below L = 2^15 take the next 16-bit word, higher lanes first:
 //   word index = next - 1 - popc(ballot & lanes_above_me);  next -= popc(ballot)
-// The word load is unconditional (every lane's address lies inside the staged 64 bytes), only
+// The word load is unconditional (every lane's address lies inside staged bytes), only
 // the state update is predicated.
-constexpr int kRing = 2048;
 constexpr int kChunk = 512;
+constexpr int kRing = 3 * kChunk;          // the ring proper
+constexpr int kRingSlot = kRing + kChunk;  // ring + the mirror below it
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -148,8 +153,17 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
   const uintptr_t lo16 = (reinterpret_cast<uintptr_t>(buf_lo) + 15) & ~static_cast<uintptr_t>(15);
   const uintptr_t hi16 = reinterpret_cast<uintptr_t>(buf_hi) & ~static_cast<uintptr_t>(15);
 
-  uint32_t state[NC], pos[NC], mprev[NC];
-  uintptr_t lo[NC];
+  // one 512-byte chunk of the stream (global address `chunk`, 512-aligned) into the ring slot at shared address
+  // `dst` of chain c, 16 bytes per lane; slot 2 goes to the mirror below the ring as well
+  auto stage = [&](int c, uint32_t dst, uintptr_t chunk) {
+    const uintptr_t a = chunk + 16 * lane;
+    if (a >= lo16 && a + 16 <= hi16) {
+      cp_async16(dst + 16 * lane, reinterpret_cast<const void *>(a));
+      if (dst == ring[c] + 2 * kChunk) cp_async16(ring[c] - kChunk + 16 * lane, reinterpret_cast<const void *>(a));
+    }
+  };
+  uint32_t state[NC], pos[NC], mprev[NC], lo_s[NC];  // lo_s: shared address of the slot holding the lowest staged chunk
+  uintptr_t lo[NC];                                  // lo: stream address of that chunk
   uint32_t end[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) end[c] = __ldg(reinterpret_cast<const uint32_t *>(stream) + grp[c]) & ~3u;  // ans/ans_decode.cl:30
@@ -162,16 +176,13 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
     const uintptr_t a_pos = top - 4 * n_lanes;  // one past the last renorm word
     // ans/ans_decode.cl:31
     state[c] = active ? __ldg(reinterpret_cast<const uint32_t *>(a_pos) + lane) : 0u;
-    // preload [c_top - kRing, c_top), c_top = a_pos rounded up to kChunk
+    // preload [c_top - kRing, c_top), c_top = a_pos rounded up to kChunk: the chunk with the first word in slot 2
     const uintptr_t c_top = (a_pos + (kChunk - 1)) & ~static_cast<uintptr_t>(kChunk - 1);
     lo[c] = c_top - kRing;
+    lo_s[c] = ring[c];
 #pragma unroll
-    for (int i = 0; i < kRing / kChunk; ++i) {
-      const uintptr_t a = lo[c] + 16 * lane + kChunk * i;
-      if (a >= lo16 && a + 16 <= hi16)
-        cp_async16(ring[c] + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
-    }
-    pos[c] = static_cast<uint32_t>(a_pos) - 2u;  // low address bits of the next word
+    for (int i = 0; i < kRing / kChunk; ++i) stage(c, ring[c] + kChunk * i, lo[c] + kChunk * i);
+    pos[c] = ring[c] + kRing - 2u - static_cast<uint32_t>(c_top - a_pos);  // shared-memory address of the next word
     mprev[c] = 0u;
   }
   cp_async_commit();
@@ -192,22 +203,25 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
     for (int j = 0; j < NC * 4; ++j) acc[j] = 0u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      // checkpoint: top up when < kRing - kChunk bytes are staged, then let the two newest groups fly.
+      // checkpoint: stage the next chunk when fewer than two are left, then let only that newest copy fly.
       // The chunk that is topped up replaces words other lanes read during the last 8 symbols.
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         pos[c] -= 2u * __popc(mprev[c] & ~gt);  // uniform again: address of the next unread word
         mprev[c] = 0u;
-        if (pos[c] + 2u - static_cast<uint32_t>(lo[c]) < static_cast<uint32_t>(kRing - kChunk)) {
+        if (pos[c] < ring[c]) pos[c] += kRing;  // it ran into the mirror during the last interval: back to slot 2
+        // bytes staged at and below the next word, in 1..kRing (pos and lo_s both live in [ring, ring + kRing))
+        int32_t staged = static_cast<int32_t>(pos[c] + 2u - lo_s[c]);
+        if (staged <= 0) staged += kRing;
+        if (staged < 2 * kChunk) {
           lo[c] -= kChunk;
-          const uintptr_t a = lo[c] + 16 * lane;
-          if (a >= lo16 && a + 16 <= hi16)
-            cp_async16(ring[c] + (a & (kRing - 1)), reinterpret_cast<const void *>(a));
+          lo_s[c] = lo_s[c] == ring[c] ? ring[c] + 2 * kChunk : lo_s[c] - kChunk;
+          stage(c, lo_s[c], lo[c]);
         }
       }
       cp_async_commit();
-      cp_async_wait_group<2>();
+      cp_async_wait_group<1>();
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -235,9 +249,7 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
           asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(sel) : "r"(mask), "r"(mprev[c]), "r"(gt));
           asm("mad.lo.u32 %0, %1, 0xfffffffe, %0;" : "+r"(pos[c]) : "r"(__popc(sel)));  // pos -= 2 popc, on the FMA pipe
           mprev[c] = mask;
-          uint32_t ra;  // (pos & (kRing - 1)) | ring in one LOP3 (the ring is kRing-aligned)
-          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ra) : "r"(pos[c]), "n"(kRing - 1), "r"(ring[c]));
-          const uint32_t w = lds_u16(ra);
+          const uint32_t w = lds_u16(pos[c]);
           uint32_t renorm;  // state << 16 | w
           asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(renorm) : "r"(state[c]), "r"(w));
           if (need) state[c] = renorm;
@@ -385,26 +397,26 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 //       when every palette of the batch has <= 65536 entries (idx < 2^16 then makes the 16-bit
 //       difference exact), else as 32 bits, in the same transposed order as sym_t:
 //       [group][k][lane][16 values].
-// Shared-memory layout of a decode CTA: n 2 KiB rings and the 8 KiB table.  The rings are indexed by OR-ing
-// low address bits into their base and so is the table, so they must be aligned to their size; the
-// dynamic shared window is only guaranteed 1 KiB alignment.  The table goes to the first 8 KiB boundary,
-// the rings fill the 2 KiB slots before and after it: n * 2 KiB + 8 KiB + at most 2 KiB of slack.
+// Shared-memory layout of a decode CTA: n rings (1.5 KiB + 512 B of mirror below each) and the 8 KiB table.  The
+// table is indexed by OR-ing low address bits into its base, so it sits on an 8 KiB boundary; the dynamic shared
+// window is only guaranteed 1 KiB alignment, and the rings (which need 16-byte alignment only) fill the space
+// before and after the table: n * 2 KiB + 8 KiB + less than 2 KiB of slack.
 struct RansSmem {
   uint32_t s0, tab, n_before;
   __device__ __forceinline__ explicit RansSmem(uint32_t base) {
-    s0 = (base + kRing - 1) & ~static_cast<uint32_t>(kRing - 1);
+    s0 = base;
     tab = (s0 + 4 * kTableSize - 1) & ~static_cast<uint32_t>(4 * kTableSize - 1);
-    n_before = (tab - s0) / kRing;
+    n_before = (tab - s0) / kRingSlot;
   }
-  __device__ __forceinline__ uint32_t ring(uint32_t i) const {
-    return i < n_before ? s0 + i * kRing : tab + 4 * kTableSize + (i - n_before) * kRing;
+  __device__ __forceinline__ uint32_t ring(uint32_t i) const {  // address of the ring proper; its mirror lies below
+    return (i < n_before ? s0 + i * kRingSlot : tab + 4 * kTableSize + (i - n_before) * kRingSlot) + kChunk;
   }
 };
 
 constexpr int kRansWarps = 8;
 constexpr int kRansChains = 2;                          // rANS groups per warp
 constexpr int kRansGroupsPerCta = kRansWarps * kRansChains;
-constexpr int kRansSmem = kRansGroupsPerCta * kRing + kTableSize * 4 + kRing;  // + alignment slack
+constexpr int kRansSmem = kRansGroupsPerCta * kRingSlot + kTableSize * 4 + kRingSlot;  // + alignment slack
 
 // CTAs of one image: [Y][chroma][palette][index]
 struct StreamGrid {
@@ -1076,7 +1088,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
 // single table: the `ans_decode` kernel of ans/ans_decode.cl:76-95 as driven by
 // ans/ans_ocl.cpp:159-345.  Output: group * n_lanes * 256 + lane * 256 + position.
 constexpr int kPlainWarps = 8;
-constexpr int kPlainSmem = kPlainWarps * kRing + kTableSize * 4 + kRing;  // + alignment slack
+constexpr int kPlainSmem = kPlainWarps * kRingSlot + kTableSize * 4 + kRingSlot;  // + alignment slack
 
 __global__ void __launch_bounds__(kPlainWarps * 32)
     ans_decode_plain_kernel(const uint32_t *__restrict__ table, const uint8_t *__restrict__ data,
