@@ -80,3 +80,35 @@ def test_encoder_argument_checks(decoder):
         gst_b200.encode_stream(decoder, np.zeros(8191, np.uint8))
     with pytest.raises(gst_b200.GstError):
         gst_b200.encode_stream(decoder, np.zeros(0, np.uint8))
+
+
+def test_many_distinct_gpu_encoded_images_in_one_batch(decoder):
+    """48 DISTINCT 512x512 containers (random symbol planes, palettes and index walks, entropy-coded by the GPU
+    encoder in a fraction of the time the CPU encoder needs) decoded in one LoadCompressedDXTs call: every
+    image against the CPU oracle."""
+    w = h = 512
+    n = (w // 4) * (h // 4)
+    files = []
+    for seed in range(48):
+        rng = np.random.default_rng(1000 + seed)
+        scale = [1.5, 4.0, 9.0, 20.0][seed % 4]
+        planes = np.clip(np.rint(rng.laplace(0.0, scale, size=6 * n)) + 128, 0, 255).astype(np.uint8)
+        entries = int(rng.integers(300, 6000))
+        pal_bytes = -(-4 * entries // 8192) * 8192
+        palette = np.zeros(pal_bytes, dtype=np.uint8)
+        palette[: 4 * entries] = rng.integers(0, 256, size=4 * entries, dtype=np.uint8)
+        # a triangle-wave fold of a random walk: every index in range, every delta within +-100
+        walk = np.cumsum(rng.integers(-100, 101, size=n))
+        period = 2 * (entries - 1)
+        m = np.mod(walk, period)
+        idx = np.where(m < entries, m, period - m)
+        deltas = np.diff(np.concatenate([[0], idx]))
+        assert np.abs(deltas).max() <= 127 + 1 and idx.min() >= 0 and idx.max() < entries
+        deltas = np.clip(deltas, -128, 127)
+        index_syms = (deltas + 128).astype(np.uint8)
+        files.append(gst_b200.build_gst(decoder, w, h, planes[: 2 * n], planes[2 * n:], palette, index_syms))
+    assert len({f.tobytes() for f in files}) == 48
+    out = decoder.DecompressDXTs(files, page=48).reshape(48, 8 * n)   # one page = one LoadCompressedDXTs call
+    for i, f in enumerate(files):
+        want = fx.oracle_decode(f, taps=False)["out"]
+        assert np.array_equal(out[i], want), f"image {i} differs from the CPU oracle"
