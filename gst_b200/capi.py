@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgst_cuda.so")
+# GST_LIB: another build of the same library (A/B timing of kernel variants, scripts/ab.sh)
+LIB_PATH = os.environ.get("GST_LIB") or os.path.join(HERE, "lib", "libgst_cuda.so")
 
 
 class GstError(RuntimeError):

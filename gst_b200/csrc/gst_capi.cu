@@ -234,6 +234,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.idx_carry = reinterpret_cast<int32_t *>(scratch + L.total_off);
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
+  gst::fill_kernel_constants(&p);
   p.tap_symbols = static_cast<uint8_t *>(taps.symbols);
   p.tap_planes = static_cast<int8_t *>(taps.planes);
   p.tap_indices = static_cast<int32_t *>(taps.indices);

@@ -136,15 +136,20 @@ __device__ __forceinline__ void cp_async_wait_group() {
 // emit(m, acc): called 16 times; acc holds the 16 symbols at positions q0 = 240 - 16m .. q0 + 15 of
 // this lane's 256-symbol run of every chain:
 //   ILV = false: acc[4c + j] = symbols q0 + 4j .. q0 + 4j + 3 of chain c, little-endian packed
-//   ILV = true (NC = 2): the two chains byte-interleaved, acc[j] = {chain 0 @ q0 + 2j, chain 1 @ q0 + 2j,
-//                chain 0 @ q0 + 2j + 1, chain 1 @ q0 + 2j + 1} -- the layout wavelet_assemble_kernel
+//   ILV = true (NC even): chains 2i and 2i + 1 byte-interleaved, acc[8i + j] = {chain 2i @ q0 + 2j, chain 2i+1 @ q0 + 2j,
+//                chain 2i @ q0 + 2j + 1, chain 2i+1 @ q0 + 2j + 1} -- the layout wavelet_assemble_kernel
 //                unpacks with one PRMT per coefficient pair; it costs nothing here because the
 //                PRMT that files a symbol away takes any destination byte.
-template <bool FULL, int NC, bool ILV, class Emit>
-__device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t *__restrict__ stream,
+#ifdef GST_STATIC_TAB
+constexpr bool kStaticTab = true;
+#else
+constexpr bool kStaticTab = false;
+#endif
+template <bool FULL, int NC, bool ILV, bool STAB, class Emit>
+__device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint32_t *tab_p, const uint8_t *__restrict__ stream,
                                                    const uint32_t (&grp)[NC], uint32_t n_lanes, const uint32_t (&ring)[NC],
                                                    const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
-  static_assert(!ILV || NC == 2, "interleaved output needs two chains");
+  static_assert(!ILV || NC % 2 == 0, "interleaved output needs pairs of chains");
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gt = lanemask_gt();
   const bool active = FULL || lane < n_lanes;
@@ -229,10 +234,18 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
         for (int c = 0; c < NC; ++c) {
           // tab_s | ((state << 2) & 0x1FFC): the shift as a multiply on the FMA pipe, one LOP3 (the table is
           // 8 KiB-aligned in the shared window) -- the mask-then-scale form costs two ALU-pipe instructions
-          uint32_t s4, slot_a;
+          uint32_t s4;
           asm("mul.lo.u32 %0, %1, 4;" : "=r"(s4) : "r"(state[c]));
-          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(slot_a) : "r"(s4), "n"(4 * kTableSize - 4), "r"(tab_s));
-          const uint32_t e = lds32(slot_a);
+          uint32_t e;
+          if (STAB) {
+            // the table is a static __shared__ array: its address is a link-time constant that rides in the
+            // immediate offset of the LDS, so the slot address is one AND and no register holds the table base
+            e = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(tab_p) + (s4 & (4 * kTableSize - 4)));
+          } else {
+            uint32_t slot_a;
+            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(slot_a) : "r"(s4), "n"(4 * kTableSize - 4), "r"(tab_s));
+            e = lds32(slot_a);
+          }
           // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  The shifts of freq and symbol
           // are written as multiplies so that they issue on the FMA pipe.  The multiply-high is left to
           // the compiler as a 64-bit product: it then folds the bias shift and the add into one
@@ -257,9 +270,10 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
           if (ILV) {
             // byte 2 (q & 1) + c of word q / 2 <- symbol
             constexpr uint32_t kIns[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};
-            const int byte = 2 * (q & 1) + c;
-            acc[q >> 1] = byte == 0 ? __byte_perm(acc[q >> 1], sym24, kIns[0]) : byte == 1 ? __byte_perm(acc[q >> 1], sym24, kIns[1])
-                        : byte == 2 ? __byte_perm(acc[q >> 1], sym24, kIns[2]) : __byte_perm(acc[q >> 1], sym24, kIns[3]);
+            const int byte = 2 * (q & 1) + (c & 1);
+            uint32_t &a = acc[8 * (c >> 1) + (q >> 1)];  // chains 2j, 2j + 1 fill words 8j .. 8j + 7
+            a = byte == 0 ? __byte_perm(a, sym24, kIns[0]) : byte == 1 ? __byte_perm(a, sym24, kIns[1])
+              : byte == 2 ? __byte_perm(a, sym24, kIns[2]) : __byte_perm(a, sym24, kIns[3]);
           } else {
             acc[4 * c + (q >> 2)] = __byte_perm(acc[4 * c + (q >> 2)], sym24, 0x2107);  // acc << 8 | symbol
           }
@@ -414,9 +428,23 @@ struct RansSmem {
 };
 
 constexpr int kRansWarps = 8;
-constexpr int kRansChains = 2;                          // rANS groups per warp
-constexpr int kRansGroupsPerCta = kRansWarps * kRansChains;
-constexpr int kRansSmem = kRansGroupsPerCta * kRingSlot + kTableSize * 4 + kRingSlot;  // + alignment slack
+// rANS groups per warp: NP plane-pair items = 2 NP chains.  NP = 2 (four chains in one instruction stream, 3 CTAs
+// = 96 chains per SM) for batches that fill the machine, NP = 1 (two chains, 5 CTAs = 80 chains per SM, twice the
+// CTAs) otherwise.
+template <int NP> struct RansCfg {
+  static constexpr int kChains = 2 * NP;
+  static constexpr int kGroupsPerCta = kRansWarps * kChains;
+#ifdef GST_STATIC_TAB
+  static constexpr int kSmem = kGroupsPerCta * kRingSlot;  // the table is a static array
+#else
+  static constexpr int kSmem = kGroupsPerCta * kRingSlot + kTableSize * 4 + kRingSlot;  // + alignment slack
+#endif
+#ifdef GST_RANS_CTAS
+  static constexpr int kCtasPerSm = GST_RANS_CTAS;
+#else
+  static constexpr int kCtasPerSm = NP == 1 ? 5 : 3;
+#endif
+};
 
 // CTAs of one image: [Y][chroma][palette][index]
 struct StreamGrid {
@@ -429,40 +457,51 @@ struct StreamGrid {
 // endpoints' planes of one colour channel, which the wavelet and the assembly process as the two
 // 16-bit halves of one register.  Stream order (codec/encoder.cpp:87,93-95): Y = Y1 || Y2,
 // chroma = Co1 || Cg1 || Co2 || Cg2, every plane groups_per_plane groups long.
-template <bool TAP>
-__device__ __forceinline__ void rans_plane_pair(const BatchParams &p, uint32_t b, uint32_t pair, uint32_t g,
-                                                const uint8_t *stream, uint32_t out_off, uint32_t tab_s, const uint32_t (&ring)[2]) {
+template <bool TAP, int NP>
+__device__ __forceinline__ void rans_plane_pairs(const BatchParams &p, uint32_t b, uint32_t type, uint32_t item0,
+                                                 const uint8_t *stream, uint32_t out_off, uint32_t tab_s, const uint32_t *tab_p, const uint32_t (&ring)[2 * NP]) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gpp = p.groups_per_plane;
-  const uint32_t grp[2] = {pair == 2 ? gpp + g : g, pair == 0 ? gpp + g : pair == 1 ? 2 * gpp + g : 3 * gpp + g};
-  uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + lane * kSymsPerLane + 240 : nullptr;
-  uint8_t *dst = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + (static_cast<size_t>(pair) * gpp + g) * (2 * kGroupSyms) +
-                 15 * 1024 + lane * 32;
-  rans_decode_groups<true, 2, true>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
-                                    [&](int m, const uint32_t (&w)[8]) {
-                                      *reinterpret_cast<uint4 *>(dst - 1024 * m) = make_uint4(w[0], w[1], w[2], w[3]);
-                                      *reinterpret_cast<uint4 *>(dst - 1024 * m + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-                                      if (TAP && tap) {
+  uint32_t grp[2 * NP];
+  uint8_t *dst[NP];
 #pragma unroll
-                                        for (int c = 0; c < 2; ++c) {
-                                          const uint32_t sel = c ? 0x7531u : 0x6420u;
-                                          *reinterpret_cast<uint4 *>(tap + static_cast<size_t>(grp[c]) * kGroupSyms - 16 * m) =
-                                              make_uint4(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel),
-                                                         __byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel));
-                                        }
-                                      }
-                                    });
+  for (int i = 0; i < NP; ++i) {
+    const uint32_t item = item0 + i;
+    const uint32_t pair = type == 0 ? 0u : 1u + item / gpp, g = item % gpp;
+    grp[2 * i] = pair == 2 ? gpp + g : g;
+    grp[2 * i + 1] = pair == 0 ? gpp + g : pair == 1 ? 2 * gpp + g : 3 * gpp + g;
+    dst[i] = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + (static_cast<size_t>(pair) * gpp + g) * (2 * kGroupSyms) + 15 * 1024 + lane * 32;
+  }
+  uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + lane * kSymsPerLane + 240 : nullptr;
+  rans_decode_groups<true, 2 * NP, true, kStaticTab>(tab_s, tab_p, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
+                                         [&](int m, const uint32_t (&w)[8 * NP]) {
+#pragma unroll
+                                           for (int i = 0; i < NP; ++i) {
+                                             *reinterpret_cast<uint4 *>(dst[i] - 1024 * m) = make_uint4(w[8 * i], w[8 * i + 1], w[8 * i + 2], w[8 * i + 3]);
+                                             *reinterpret_cast<uint4 *>(dst[i] - 1024 * m + 16) = make_uint4(w[8 * i + 4], w[8 * i + 5], w[8 * i + 6], w[8 * i + 7]);
+                                             if (TAP && tap) {
+#pragma unroll
+                                               for (int c = 0; c < 2; ++c) {
+                                                 const uint32_t sel = c ? 0x7531u : 0x6420u;
+                                                 *reinterpret_cast<uint4 *>(tap + static_cast<size_t>(grp[2 * i + c]) * kGroupSyms - 16 * m) =
+                                                     make_uint4(__byte_perm(w[8 * i], w[8 * i + 1], sel), __byte_perm(w[8 * i + 2], w[8 * i + 3], sel),
+                                                                __byte_perm(w[8 * i + 4], w[8 * i + 5], sel), __byte_perm(w[8 * i + 6], w[8 * i + 7], sel));
+                                               }
+                                             }
+                                           }
+                                         });
 }
 
 // One warp's share of the palette or index stream: NC consecutive groups starting at `group`.
-template <int NC, bool TAP>
+template <int NC, bool TAP, int NA>
 __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_t b, uint32_t type, uint32_t group,
                                                    const uint8_t *stream, uint32_t out_off, uint32_t pal_off,
-                                                   uint32_t tab_s, const uint32_t (&ring2)[2]) {
+                                                   uint32_t tab_s, const uint32_t *tab_p, const uint32_t (&ring_all)[NA]) {
+  static_assert(NC <= NA, "not enough rings");
   const uint32_t lane = threadIdx.x & 31;
   uint32_t grp[NC], ring[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) ring[c] = ring2[c];
+  for (int c = 0; c < NC; ++c) ring[c] = ring_all[c];
 
 #pragma unroll
   for (int c = 0; c < NC; ++c) grp[c] = group + c;
@@ -472,7 +511,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
     const uint64_t off = static_cast<uint64_t>(pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
     const bool ok = off + NC * kGroupSyms <= p.palette_cap;
     uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
-    rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
+    rans_decode_groups<true, NC, false, kStaticTab>(tab_s, tab_p, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                         [&](int m, const uint32_t (&w)[NC * 4]) {
 #pragma unroll
                                           for (int c = 0; c < NC; ++c) {
@@ -491,7 +530,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
   const bool idx16 = p.idx16 != 0;
-  rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
+  rans_decode_groups<true, NC, false, kStaticTab>(tab_s, tab_p, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                [&](int m, const uint32_t (&wa)[NC * 4]) {
 #pragma unroll
                                  for (int c = 0; c < NC; ++c) {
@@ -536,13 +575,25 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   }
 }
 
-template <bool TAP>
-__global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+template <bool TAP, int NP>
+__global__ void __launch_bounds__(kRansWarps * 32, RansCfg<NP>::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+  constexpr int NC = RansCfg<NP>::kChains;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const RansSmem lay(smem_u32(smem));
   const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t ring[2] = {lay.ring(2 * warp), lay.ring(2 * warp + 1)};
+  uint32_t ring[NC];
+#ifdef GST_STATIC_TAB
+  __shared__ __align__(16) uint32_t s_tab[kTableSize];
+  const uint32_t *tab_p = s_tab;
+  const uint32_t tab_s = smem_u32(s_tab);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) ring[c] = smem_u32(smem) + (NC * warp + c) * kRingSlot + kChunk;
+#else
+  const RansSmem lay(smem_u32(smem));
+#pragma unroll
+  for (int c = 0; c < NC; ++c) ring[c] = lay.ring(NC * warp + c);
   const uint32_t tab_s = lay.tab;
+  const uint32_t *tab_p = nullptr;
+#endif
 
   const uint32_t per_image = sg.per_image();
   const uint32_t b = blockIdx.x / per_image;
@@ -560,26 +611,35 @@ __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const 
   if (type < 2) {
     // work items of a plane stream: (pair, group); Y has groups_per_plane of them, chroma twice as many
     const uint32_t n_items = (type + 1) * p.groups_per_plane;
-    if (r * kRansWarps >= n_items) return;
+    if (r * kRansWarps * NP >= n_items) return;
     load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
     __syncthreads();
-    const uint32_t item = r * kRansWarps + warp;
+    const uint32_t item = (r * kRansWarps + warp) * NP;
     if (item >= n_items) return;
-    const uint32_t pair = type == 0 ? 0u : 1u + item / p.groups_per_plane;
-    rans_plane_pair<TAP>(p, b, pair, item % p.groups_per_plane, stream, out_off, tab_s, ring);
+    if (NP == 1 || item + 1 < n_items) {
+      rans_plane_pairs<TAP, NP>(p, b, type, item, stream, out_off, tab_s, tab_p, ring);
+    } else {
+      const uint32_t ring1[2] = {ring[0], ring[1]};
+      rans_plane_pairs<TAP, 1>(p, b, type, item, stream, out_off, tab_s, tab_p, ring1);
+    }
     return;
   }
   const uint32_t n_groups = type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
-  const uint32_t first = r * kRansGroupsPerCta;
+  const uint32_t first = r * RansCfg<NP>::kGroupsPerCta;
   if (first >= n_groups) return;
   load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
   __syncthreads();
-  const uint32_t group = first + warp * kRansChains;
+  const uint32_t group = first + warp * NC;
   if (group >= n_groups) return;
-  if (group + 1 < n_groups)
-    rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring);
-  else
-    rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, ring);
+  const uint32_t left = n_groups - group;
+  if (NC == 4 && left >= 4) {
+    rans_stream_groups<NC, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, tab_p, ring);
+  } else {
+    // tail: two chains at a time, then one
+    if (left >= 2) rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, tab_p, ring);
+    if (NC == 4 && left == 3) rans_stream_groups<1, TAP>(p, b, type, group + 2, stream, out_off, is.pal_off, tab_s, tab_p, ring);
+    if (left == 1) rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, tab_p, ring);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -609,7 +669,6 @@ __global__ void __launch_bounds__(kRansWarps * 32, 5) rans_streams_kernel(const 
 constexpr int kBias = 4096;
 constexpr int kRaw = 0x1080;
 __host__ __device__ constexpr uint32_t pk(int v) { return static_cast<uint32_t>(v) * 65537u; }  // v in both halves
-constexpr uint32_t kOnes = 0x00010001u;
 
 __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b) {  // a + b on the FMA pipe
   uint32_t d;
@@ -627,7 +686,27 @@ __device__ __forceinline__ uint32_t fma_sub_from(uint32_t a, uint32_t b) {  // b
 // and so was the sign-bit shift (T >> 13) as a multiply-high (1 %): IMAD.HI is quarter rate and the
 // FMA-heavy pipe becomes the bound.  The /4 quotient as a plain shift, or the adds left to ptxas, are
 // 1-2 % slower the other way (ALU pipe).
-struct ShiftK { uint32_t k30, k31; };
+// Constants the kernel wants in registers / the constant bank (BatchParams::kc): as literals ptxas rematerialises
+// them with a MOV before every use, and VIADDMNMX takes one immediate only.
+//   r3 = ph(3), r1 = ph(1): round-toward-zero addends;  k31 = 2^31 (as a parameter it stays an IMAD.HI on the FMA
+//   pipe; as a literal ptxas folds the shift and the add after it into one ALU-pipe LEA.HI);
+//   cb / cb3 = ph(2) / ph(5), cr / cr3 = ph(-254) / ph(-251): dividend offsets for high-band operands of bias kBias / kRaw
+struct ShiftK { uint32_t k30, k31, r3, r1, cb, cb3, cr, cr3; };
+__host__ __device__ constexpr uint32_t ph(int v) { return (static_cast<uint32_t>(v) & 0xFFFFu) * 65537u; }  // per-half constant
+// Round-toward-zero correction of a packed dividend without a sign test: with T = t + B in each half (B a multiple
+// of the divisor k = R + 1, |t| < B) the value  max(T, min(T + R, B + R))  is T + R for t < 0 and has the same
+// floor(. / k) as T for t >= 0, so that floor(result / k) = trunc(t / k) + B / k.  Two packed 16-bit min/max
+// instructions (VIADDMNMX.S16x2 + VIMNMX.S16x2) replace the shift + mask + multiply-add of the sign-bit form.
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <int R, int B>
+__device__ __forceinline__ uint32_t trunc_fix(uint32_t T, const ShiftK &sk) {
+  return max16x2(T, __viaddmin_s16x2(T, R == 3 ? sk.r3 : sk.r1, ph(B + R)));
+}
+
 __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t k) {
   uint32_t d;
   asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(k));
@@ -635,19 +714,20 @@ __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t k) {
 }
 
 // d[2x] = s[x] - (h[x-1] + h[x] + 2) / 4.  HB = bias of the h operands; cD = pk(2048 + kBias - bias of S).
+// The dividend T = t + 2^13 = (HP + HN) + c with c = 2 + 2^13 - 2 HB; c rides in the add of the two min / max
+// instructions, so the sum itself is one FMA-pipe add:  T3 = max(U + c, min(U + c + 3, 2^13 + 3)).
 template <int HB>
 __device__ __forceinline__ uint32_t lift_even_p(uint32_t S, uint32_t HP, uint32_t HN, uint32_t cD, const ShiftK &sk) {
-  const uint32_t T = HP + HN + pk(2 + 8192 - 2 * HB);     // t + 2^13
-  const uint32_t neg = ~(T >> 13) & kOnes;                // [t < 0]
-  const uint32_t T3 = neg * 3u + T;                       // trunc(t / 4) = floor((t + 3 [t < 0]) / 4)
+  const uint32_t U = fma_add(HP, HN);
+  const uint32_t m = __viaddmin_s16x2(U, HB == kBias ? sk.cb3 : sk.cr3, ph(8192 + 3));
+  const uint32_t T3 = __viaddmax_s16x2(U, HB == kBias ? sk.cb : sk.cr, m);
   const uint32_t Q = mulhi(T3 & 0xFFFCFFFCu, sk.k30);     // trunc(t / 4) + 2048
   return S - Q + cD;
 }
 // d[2x+1] = h[x] + (d[2x] + d[2x+2]) / 2.  The d operands are computed values (bias kBias); cH = pk(-bias of H).
 __device__ __forceinline__ uint32_t lift_odd_p(uint32_t H, uint32_t EP, uint32_t EN, uint32_t cH, const ShiftK &sk) {
   const uint32_t T = fma_add(EP, EN);                     // t + 2^13
-  const uint32_t neg = ~(T >> 13) & kOnes;                // [t < 0]
-  const uint32_t T2 = fma_add(T, neg);                    // trunc(t / 2) = floor((t + [t < 0]) / 2)
+  const uint32_t T2 = trunc_fix<1, 8192>(T, sk);
   const uint32_t X = mulhi(T2 & 0xFFFEFFFEu, sk.k31);     // trunc(t / 2) + 4096
   return H + X + cH;
 }
@@ -800,13 +880,11 @@ __device__ __forceinline__ void low_level_p(uint32_t w_s, uint32_t lane, uint32_
 __device__ __forceinline__ void ycocg_to_rgb_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk, uint32_t &R, uint32_t &G,
                                                uint32_t &Bq) {
   const uint32_t Tn = fma_sub_from(CG, pk(384));                      // -cg + 256; trunc(-cg / 2) = -trunc(cg / 2)
-  const uint32_t n1 = ~(Tn >> 8) & kOnes;                             // [-cg < 0]
-  const uint32_t X1 = mulhi(fma_add(Tn, n1) & 0xFFFEFFFEu, sk.k31);   // trunc(-cg / 2) + 128
+  const uint32_t X1 = mulhi(trunc_fix<1, 256>(Tn, sk) & 0xFFFEFFFEu, sk.k31);   // trunc(-cg / 2) + 128
   const uint32_t Tb = fma_add(Y, X1);                                 // (y + 128) + ... = t + 256
   G = CG + Tb + pk(2048 - 128 - 256);
   const uint32_t V = Tb - CO + pk(512 - 256 + 128);                   // (t - co) + 512
-  const uint32_t n2 = ~(V >> 9) & kOnes;
-  const uint32_t X2 = mulhi(fma_add(V, n2) & 0xFFFEFFFEu, sk.k31);    // trunc((t - co) / 2) + 256
+  const uint32_t X2 = mulhi(trunc_fix<1, 512>(V, sk) & 0xFFFEFFFEu, sk.k31);    // trunc((t - co) / 2) + 256
   Bq = fma_add(X2, pk(32768 - 256));
   R = Bq + CO + pk(512 - 32768 - 128);
 }
@@ -833,7 +911,11 @@ __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t 
 //             stores; palette index = run_end - S.  The index / palette loads of the next slab
 //             are in flight while a slab is assembled, those of slab 0 during the wavelet.
 constexpr int kWaWarps = 2;
+#ifdef GST_WA_PAD
+constexpr int kWaSmem = kWaWarps * kWarpWork + GST_WA_PAD;  // occupancy experiment
+#else
 constexpr int kWaSmem = kWaWarps * kWarpWork;  // 24576
+#endif
 
 // IDX16: the index suffix sums are u16 (every palette of the batch has <= 65536 entries), else u32.
 template <int RGB, bool TAP, bool IDX16>
@@ -936,7 +1018,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   asm volatile("" : "+r"(k10));  // keep it in a register (PRMT takes no immediate source)
   cp_async_wait_group<0>();
   __syncwarp();
-  const ShiftK sk{1u << 30, 1u << 31};
+  // r3 / r1 come from the kernel parameters: as literals ptxas rematerialises them with a MOV before every use
+  const ShiftK sk{1u << 30, 1u << 31, p.kc[0], p.kc[1], p.kc[3], p.kc[4], p.kc[5], p.kc[6]};
   low_level_p<2>(w_s, lane, k10, sk);
   low_level_p<4>(w_s, lane, k10, sk);
   low_level_p<8>(w_s, lane, k10, sk);
@@ -1106,7 +1189,7 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
   const bool active = lane < n_lanes;
   const uint32_t grp[1] = {group};
   const uint32_t ring[1] = {lay.ring(warp)};
-  rans_decode_groups<false, 1, false>(tab_s, data, grp, n_lanes, ring, data, data + data_bytes,
+  rans_decode_groups<false, 1, false, false>(tab_s, nullptr, data, grp, n_lanes, ring, data, data + data_bytes,
                                       [&](int m, const uint32_t (&w)[4]) {
                                         if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w[0], w[1], w[2], w[3]);
                                       });
@@ -1219,9 +1302,14 @@ static cudaError_t ensure_attrs() {
                     wavelet_assemble_kernel<0, true, false>, wavelet_assemble_kernel<1, true, false>}) {
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem)) != cudaSuccess) return e;
     }
-    for (auto *k : {rans_streams_kernel<false>, rans_streams_kernel<true>}) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kRansSmem)) != cudaSuccess) return e;
+    for (auto *k : {rans_streams_kernel<false, 1>, rans_streams_kernel<true, 1>}) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RansCfg<1>::kSmem)) != cudaSuccess) return e;
     }
+#if defined(GST_RANS_NP) && GST_RANS_NP == 2
+    for (auto *k : {rans_streams_kernel<false, 2>, rans_streams_kernel<true, 2>}) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RansCfg<2>::kSmem)) != cudaSuccess) return e;
+    }
+#endif
     return cudaFuncSetAttribute(ans_decode_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem);
   }();
   return once;
@@ -1241,17 +1329,24 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
+  // Two chains per warp (NP = 1).  Four chains per warp at 3 CTAs per SM (96 chains instead of 80, -DGST_RANS_NP=2)
+  // was measured 10 % slower: the kernel wants warps, not chains per warp.
+#ifdef GST_RANS_NP
+  constexpr int np = GST_RANS_NP;
+#else
+  constexpr int np = 1;
+#endif
+  const uint32_t items_per_cta = kRansWarps * np, groups_per_cta = kRansWarps * 2 * np;
   StreamGrid sg;
-  sg.y_ctas = (p.groups_per_plane + kRansWarps - 1) / kRansWarps;      // one (plane pair, group) per warp
-  sg.c_ctas = (2 * p.groups_per_plane + kRansWarps - 1) / kRansWarps;
-  sg.pal_ctas = (max_palette_bytes / kGroupSyms + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
-  sg.idx_ctas = (p.groups_per_plane + kRansGroupsPerCta - 1) / kRansGroupsPerCta;
+  sg.y_ctas = (p.groups_per_plane + items_per_cta - 1) / items_per_cta;      // NP (plane pair, group) items per warp
+  sg.c_ctas = (2 * p.groups_per_plane + items_per_cta - 1) / items_per_cta;
+  sg.pal_ctas = (max_palette_bytes / kGroupSyms + groups_per_cta - 1) / groups_per_cta;
+  sg.idx_ctas = (p.groups_per_plane + groups_per_cta - 1) / groups_per_cta;
   // the stage taps (parity tests only) are a separate instantiation: the production kernels carry none of that code
   const bool taps = p.tap_symbols || p.tap_planes || p.tap_indices;
-  if (taps)
-    rans_streams_kernel<true><<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
-  else
-    rans_streams_kernel<false><<<p.n_images * sg.per_image(), kRansWarps * 32, kRansSmem, s>>>(p, sg);
+  const uint32_t rans_grid = p.n_images * sg.per_image();
+  if (taps) rans_streams_kernel<true, np><<<rans_grid, kRansWarps * 32, RansCfg<np>::kSmem, s>>>(p, sg);
+  else rans_streams_kernel<false, np><<<rans_grid, kRansWarps * 32, RansCfg<np>::kSmem, s>>>(p, sg);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;

@@ -70,11 +70,18 @@ struct BatchParams {
   int32_t *idx_carry;        // [B][N/8192] sum of the index groups BEFORE each group (accumulated with atomics)
   // outputs
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
+  uint32_t kc[8];            // packed constants the wavelet kernel wants in the constant bank (fill_kernel_constants)
   // optional taps for the stage parity tests (NULL in production)
   uint8_t *tap_symbols;      // reference decmp_buf layout: image b stream s at out_off[4b+s]
   int8_t *tap_planes;        // [B][6][N] raster planes (codec/decoder.cpp:280)
   int32_t *tap_indices;      // [B][N] final palette indices (codec/decoder.cpp:302)
 };
+
+inline void fill_kernel_constants(BatchParams *p) {
+  auto ph = [](int v) { return (static_cast<uint32_t>(v) & 0xFFFFu) * 65537u; };
+  p->kc[0] = ph(3); p->kc[1] = ph(1); p->kc[2] = 1u << 31; p->kc[3] = ph(2); p->kc[4] = ph(5);
+  p->kc[5] = ph(-254); p->kc[6] = ph(-251); p->kc[7] = 0x10101010u;
+}
 
 // launch helpers (gst_kernels.cu)
 cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,

@@ -61,6 +61,20 @@ BENCH_KERNEL(k_iadd3, asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0
 BENCH_KERNEL(k_imax, asm volatile("max.s32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
 BENCH_KERNEL(k_sar_fix, { int x = (int)v[j]; x = x / 4; v[j] = (uint32_t)x + k; })
 
+BENCH_KERNEL(k_viaddmnmx, v[j] = __viaddmin_s16x2_relu(v[j], k, c);)
+BENCH_KERNEL(k_viaddmnmx_u, v[j] = __viaddmin_u16x2(v[j], k, c);)
+BENCH_KERNEL(k_vimnmx3, v[j] = __vimax3_s16x2(v[j], k, c);)
+BENCH_KERNEL(k_mix_lop_viaddmnmx, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); v[j] = __viaddmin_s16x2_relu(v[j], k, c);)
+BENCH_KERNEL(k_mix_imad_viaddmnmx, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c)); v[j] = __viaddmin_s16x2_relu(v[j], k, c);)
+BENCH_KERNEL(k_mix_iadd_viaddmnmx, asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); v[j] = __viaddmin_s16x2_relu(v[j], k, c);)
+BENCH_KERNEL(k_mix_lop_vimnmx3, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); v[j] = __vimax3_s16x2(v[j], k, c);)
+BENCH_KERNEL(k_iadd3_only, asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t; }" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_lea_hi, asm volatile("{ .reg .u32 t; shr.u32 t, %0, 31; add.u32 %0, t, %1; }" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_lop_lea, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("{ .reg .u32 t; shl.b32 t, %0, 3; add.u32 %0, t, %1; }" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_imad_iadd, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_mix_lop_iadd_imad, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_isetp_only, { uint32_t t; asm volatile("{ .reg .pred p; setp.lt.u32 p, %1, %2; selp.u32 %0, %1, %2, p; }" : "=r"(t) : "r"(v[j]), "r"(c)); v[j] = t; })
+
 __global__ void __launch_bounds__(1024) k_lds(uint32_t *out, uint32_t seed) {
   __shared__ uint32_t tab[2048];
   for (int i = threadIdx.x; i < 2048; i += 1024) tab[i] = (i * 2654435761u + seed) & 2047;
@@ -101,7 +115,12 @@ int main() {
       {"IMAD+HADD2 alternating", k_mix_imad_hadd2, 2}, {"LOP3+SHFL alternating", k_mix_lop_shfl, 2},
       {"LOP3+IMAD+FFMA", k_mix3, 3}, {"VIADD.16x2 (add.s16x2)", k_viadd16x2, 1}, {"VIMNMX.16x2 (max.s16x2)", k_vimnmx16x2, 1},
       {"LOP3+VIADD.16x2 alternating", k_mix_lop_viadd16x2, 2}, {"IMAD+VIADD.16x2 alternating", k_mix_imad_viadd16x2, 2},
-      {"LOP3+VIMNMX.16x2 alternating", k_mix_lop_vimnmx16x2, 2}, {"VIMNMX (max.s32)", k_imax, 1}, {"SHL+ADD (LEA?)", k_lea, 1}, {"x/4 signed (+IADD)", k_sar_fix, 1}};
+      {"LOP3+VIMNMX.16x2 alternating", k_mix_lop_vimnmx16x2, 2}, {"VIMNMX (max.s32)", k_imax, 1}, {"SHL+ADD (LEA?)", k_lea, 1}, {"x/4 signed (+IADD)", k_sar_fix, 1},
+      {"VIADDMNMX.S16x2.RELU", k_viaddmnmx, 1}, {"VIADDMNMX.U16x2", k_viaddmnmx_u, 1}, {"VIMNMX3.S16x2", k_vimnmx3, 1},
+      {"LOP3+VIADDMNMX alternating", k_mix_lop_viaddmnmx, 2}, {"IMAD+VIADDMNMX alternating", k_mix_imad_viaddmnmx, 2},
+      {"IADD+VIADDMNMX alternating", k_mix_iadd_viaddmnmx, 2}, {"LOP3+VIMNMX3 alternating", k_mix_lop_vimnmx3, 2},
+      {"IADD3 (2 adds)", k_iadd3_only, 1}, {"SHR31+ADD (LEA.HI?)", k_lea_hi, 1}, {"LOP3+LEA alternating", k_mix_lop_lea, 2},
+      {"IMAD+IADD alternating", k_mix_imad_iadd, 2}, {"LOP3+IADD+IMAD", k_mix_lop_iadd_imad, 3}, {"SETP+SELP", k_isetp_only, 2}};
   printf("device %s, %d SMs, clock attr %d kHz\n", prop.name, sms, khz);
   printf("%-34s %12s %16s\n", "instruction", "ms", "thread-ops/clk/SM");
   for (auto &e : ks) {
