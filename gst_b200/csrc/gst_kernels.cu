@@ -707,6 +707,14 @@ __device__ __forceinline__ uint32_t trunc_fix(uint32_t T, const ShiftK &sk) {
   return max16x2(T, __viaddmin_s16x2(T, R == 3 ? sk.r3 : sk.r1, ph(B + R)));
 }
 
+// (a >> SH) + c as ONE instruction: written as a multiply-high by 2^(32 - SH) with an addend, which ptxas turns
+// into LEA.HI (shift + add).  Left to the compiler as C the expression becomes SHF + LOP3 + IADD3.
+template <int SH>
+__device__ __forceinline__ uint32_t shr_add(uint32_t a, uint32_t c) {
+  uint32_t d;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(1u << (32 - SH)), "r"(c));
+  return d;
+}
 __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t k) {
   uint32_t d;
   asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(k));
@@ -721,15 +729,16 @@ __device__ __forceinline__ uint32_t lift_even_p(uint32_t S, uint32_t HP, uint32_
   const uint32_t U = fma_add(HP, HN);
   const uint32_t m = __viaddmin_s16x2(U, HB == kBias ? sk.cb3 : sk.cr3, ph(8192 + 3));
   const uint32_t T3 = __viaddmax_s16x2(U, HB == kBias ? sk.cb : sk.cr, m);
-  const uint32_t Q = mulhi(T3 & 0xFFFCFFFCu, sk.k30);     // trunc(t / 4) + 2048
-  return S - Q + cD;
+  // Q - cD = (T3 >> 2) - cD is one LEA.HI (shift + add), and S - (Q - cD) one FMA-pipe add.  (A multiply-high for
+  // the shift was measured 4 % slower: IMAD.HI costs far more than its four issue cycles on the FMA-heavy pipe.)
+  const uint32_t Qc = shr_add<2>(T3 & 0xFFFCFFFCu, 0u - cD);   // trunc(t / 4) + 2048 - cD
+  return fma_sub_from(Qc, S);
 }
 // d[2x+1] = h[x] + (d[2x] + d[2x+2]) / 2.  The d operands are computed values (bias kBias); cH = pk(-bias of H).
 __device__ __forceinline__ uint32_t lift_odd_p(uint32_t H, uint32_t EP, uint32_t EN, uint32_t cH, const ShiftK &sk) {
   const uint32_t T = fma_add(EP, EN);                     // t + 2^13
   const uint32_t T2 = trunc_fix<1, 8192>(T, sk);
-  const uint32_t X = mulhi(T2 & 0xFFFEFFFEu, sk.k31);     // trunc(t / 2) + 4096
-  return H + X + cH;
+  return shr_add<1>(T2 & 0xFFFEFFFEu, H) + cH;            // h + trunc(t / 2) + 4096 - bias of H
 }
 // 1-D inverse 5/3 lifting of v = [low half | high half] in registers, codec/inverse_wavelet.cl:28-64
 // (NormalizeIndex mirror resolved at compile time).  HB = bias of the high half; the result has bias kBias.
@@ -873,20 +882,27 @@ __device__ __forceinline__ void low_level_p(uint32_t w_s, uint32_t lane, uint32_
   __syncwarp();
 }
 
+// The fields the wavelet stores for the assembly are (int8 value + 128) + a multiple of 256 that costs nothing (it is
+// part of the XOR constant of the (char) truncation) and is chosen so that no step of the colour conversion needs
+// an add of its own for a constant:
+constexpr int kBY = 1024, kBO = 0, kBG = 512;
+constexpr int kB1 = 512;                             // bias of the dividend -cg
+constexpr int kB2 = 256 + kBY - kBO;                 // bias of the dividend t - co
+constexpr int kBiasG = 256 + kBG + kBY + kB1 / 2;    // g + kBiasG: a multiple of 2048, so that (g + bias) << 5 only spills into masked bits
+constexpr int kBiasR = 32768 + 128 + kBO;            // r + kBiasR: a multiple of 32
+static_assert(kBiasG % 2048 == 0 && kBiasR % 32 == 0 && kB2 % 2 == 0 && kB2 >= 512, "colour conversion biases");
 // codec/assemble.cl:39-62 for both endpoints at once: YCoCg667 -> RGB565 with truncating division and
 // an unmasked shift/or pack.  Inputs: (int8 value + 128) of plane A | plane B << 16.
 //   t = y - cg / 2;  g = cg + t;  b = (t - co) / 2;  r = b + co;  out = r << 11 | g << 5 | b  (low 16 bits)
-// Outputs (per half): R = r + 512, G = g + 2048, Bq = b + 32768.
+// Outputs (per half): R = r + kBiasR, G = g + kBiasG, Bq = b + 32768.
 __device__ __forceinline__ void ycocg_to_rgb_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk, uint32_t &R, uint32_t &G,
                                                uint32_t &Bq) {
-  const uint32_t Tn = fma_sub_from(CG, pk(384));                      // -cg + 256; trunc(-cg / 2) = -trunc(cg / 2)
-  const uint32_t X1 = mulhi(trunc_fix<1, 256>(Tn, sk) & 0xFFFEFFFEu, sk.k31);   // trunc(-cg / 2) + 128
-  const uint32_t Tb = fma_add(Y, X1);                                 // (y + 128) + ... = t + 256
-  G = CG + Tb + pk(2048 - 128 - 256);
-  const uint32_t V = Tb - CO + pk(512 - 256 + 128);                   // (t - co) + 512
-  const uint32_t X2 = mulhi(trunc_fix<1, 512>(V, sk) & 0xFFFEFFFEu, sk.k31);    // trunc((t - co) / 2) + 256
-  Bq = fma_add(X2, pk(32768 - 256));
-  R = Bq + CO + pk(512 - 32768 - 128);
+  const uint32_t Tn = fma_sub_from(CG, pk(kB1 + 128 + kBG));          // -cg + kB1; trunc(-cg / 2) = -trunc(cg / 2)
+  const uint32_t Tb = shr_add<1>(trunc_fix<1, kB1>(Tn, sk) & 0xFFFEFFFEu, Y);   // t + kB1 / 2 + 128 + kBY
+  G = fma_add(CG, Tb);                                                // g + kBiasG
+  const uint32_t V = fma_sub_from(CO, Tb);                            // (t - co) + kB2
+  Bq = shr_add<1>(trunc_fix<1, kB2>(V, sk) & 0xFFFEFFFEu, pk(32768 - kB2 / 2));  // b + 32768
+  R = fma_add(Bq, CO);                                                // r + kBiasR
 }
 __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk) {  // ep1 | ep2 << 16
   uint32_t R, G, Bq;
@@ -1062,8 +1078,9 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
       for (int i = 0; i < 32; ++i) v[i] = lds32(wp + off[i & 7] + i * 128);
       inverse_lift_p<32, kBias>(v, pk(2048), sk);
       // (char) truncation: low byte of (x + 4096) = x mod 256; ^ 0x80 makes it (int8) x + 128
+      const uint32_t kx = pl == 0 ? ph(128 + kBY) : pl == 1 ? ph(128 + kBO) : ph(128 + kBG);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sts32(wp + off[i & 7] + i * 128, (v[i] & 0x00FF00FFu) ^ 0x00800080u);
+      for (int i = 0; i < 32; ++i) sts32(wp + off[i & 7] + i * 128, (v[i] & 0x00FF00FFu) ^ kx);
       if (TAP && p.tap_planes) {
         // reference plane order [Y1, Y2, Co1, Cg1, Co2, Cg2]: pair 0 = planes (0, 1), pair 1 = (2, 4), pair 2 = (3, 5)
         const uint32_t pa = pl == 0 ? 0 : pl == 1 ? 2 : 3, pb = pl == 0 ? 1 : pl == 1 ? 4 : 5;
@@ -1115,8 +1132,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
       for (int j = 0; j < 4; ++j) {
         uint32_t R, G, Bq;
         ycocg_to_rgb_p(Y[j], CO[j], CG[j], sk, R, G, Bq);
-        int c0[3] = {static_cast<int>(R & 0xFFFFu) - 512, static_cast<int>(G & 0xFFFFu) - 2048, static_cast<int>(Bq & 0xFFFFu) - 32768};
-        int c1[3] = {static_cast<int>(R >> 16) - 512, static_cast<int>(G >> 16) - 2048, static_cast<int>(Bq >> 16) - 32768};
+        int c0[3] = {static_cast<int>(R & 0xFFFFu) - kBiasR, static_cast<int>(G & 0xFFFFu) - kBiasG, static_cast<int>(Bq & 0xFFFFu) - 32768};
+        int c1[3] = {static_cast<int>(R >> 16) - kBiasR, static_cast<int>(G >> 16) - kBiasG, static_cast<int>(Bq >> 16) - 32768};
         c0[0] = static_cast<int>((static_cast<uint32_t>(c0[0]) << 3) | static_cast<uint32_t>(c0[0] >> 2));
         c0[1] = static_cast<int>((static_cast<uint32_t>(c0[1]) << 2) | static_cast<uint32_t>(c0[1] >> 4));
         c0[2] = static_cast<int>((static_cast<uint32_t>(c0[2]) << 3) | static_cast<uint32_t>(c0[2] >> 2));
