@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t sext_byte_pair(uint32_t w) {
 // the address back -- the checkpoint does it (+1536 when it has left the ring).
 //
 // Per symbol and lane (ans/ans_decode.cl:38-65):
-//   e = table[state & 2047];  state = (state >> 11) * e.freq + slot - e.cum   (as umulhi, see gst_kernels.cuh)
+//   e = table[state & 2047];  state = (state >> 11) * e.freq + slot - e.cum   (entry layout: gst_kernels.cuh)
 //   lanes whose state fell below L = 2^15 take the next 16-bit word, higher lanes first:
 //   word index = next - 1 - popc(ballot & lanes_above_me);  next -= popc(ballot)
 // The word load is unconditional (every lane's address lies inside staged bytes), only
@@ -246,16 +246,11 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint32_
             asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(slot_a) : "r"(s4), "n"(4 * kTableSize - 4), "r"(tab_s));
             e = lds32(slot_a);
           }
-          // state' = umulhi(state, freq << 21) + bias' (gst_kernels.cuh).  The shifts of freq and symbol
-          // are written as multiplies so that they issue on the FMA pipe.  The multiply-high is left to
-          // the compiler as a 64-bit product: it then folds the bias shift and the add into one
-          // LEA.HI.SX32 (hi + (e >> 19)), where the mul.hi/add form makes ptxas put the bias in the
-          // 64-bit addend of IMAD.HI and re-zero the low half of that register pair every step.
-          uint32_t f21, sym24;
-          asm("mul.lo.u32 %0, %1, 2097152;" : "=r"(f21) : "r"(e));   // e << 21
-          asm("mul.lo.u32 %0, %1, 8192;" : "=r"(sym24) : "r"(e));    // e << 13: symbol in the top byte
-          state[c] = static_cast<uint32_t>((static_cast<uint64_t>(state[c]) * f21) >> 32) +
-                     static_cast<uint32_t>(static_cast<int32_t>(e) >> 19);
+          // state' = (state >> 11) * freq + slot - cum (gst_kernels.cuh); the symbol shift is a multiply so that it
+          // issues on the FMA pipe
+          uint32_t sym24;
+          asm("mul.lo.u32 %0, %1, 4096;" : "=r"(sym24) : "r"(e));    // e << 12: symbol in the top byte
+          state[c] = (state[c] >> 11) * (e & 0xFFFu) + (e >> 20);
           const bool need = FULL ? (state[c] < kRansL) : (active && state[c] < kRansL);
           const uint32_t mask = __ballot_sync(0xffffffffu, need);
           uint32_t sel;  // (mask & gt) | (mprev & ~gt)
@@ -657,15 +652,17 @@ __global__ void __launch_bounds__(kRansWarps * 32, RansCfg<NP>::kCtasPerSm) rans
 // Every wavelet intermediate is bounded by |x| <= 3488 for ANY input bytes (128 + 672 per level), so
 // halves stay in [608, 7712]: non-negative, and sums of three never reach 2^16 -- plain 32-bit adds
 // never carry across the halves.  The reference's truncating divisions
-// (codec/inverse_wavelet.cl:28-64, '/' on ints) are done on T = t + 2^13 (t = the dividend, |t| < 2^13):
-// bit 13 of T is [t >= 0], which gives the round-toward-zero correction without a per-half sign
-// extension, and the bits a 32-bit shift would carry from the high half into the low half are
-// masked off before the shift.
+// (codec/inverse_wavelet.cl:28-64, '/' on ints) are done on T = t + B (t = the dividend, |t| < B, B a multiple of
+// the divisor): trunc_fix() below turns T into a value whose FLOOR quotient is trunc(t / k) + B / k with two packed
+// 16-bit min / max instructions, the bits a 32-bit shift would carry from the high half into the low half are masked
+// off, and the shift itself rides in a LEA.HI together with the add that follows it.
 //
-// Pipes: every LOP3 / SHF / IADD3 / PRMT occupies the ALU pipe for two cycles per warp, and that
-// pipe -- not the issue slots -- bounds this kernel (profiles/: ALU 81 % busy, FMA pipe 15 %, before
-// this was done).  So whatever has a multiplier form is written as one: two-input adds as
-// mad.lo(a, 1, b) (IMAD.IADD), the shifts that produce the quotient as mul.hi by 2^30 / 2^31 (IMAD.HI).
+// Pipes (profiles/pipe_rates_b200.txt): LOP3 / SHF / PRMT / IADD3 / LEA / VIADDMNMX occupy the ALU pipe for two
+// cycles per warp (two-input IADD, VIMNMX: one), IMAD the FMA-heavy pipe for two, and the ALU pipe -- not the issue
+// slots -- bounds this kernel.  So two-input adds are written as mad.lo(a, 1, b) (IMAD.IADD) and constants are
+// folded into instructions that are there anyway (the add of VIADDMNMX, the addend of LEA.HI, the free multiple of
+// 256 in the fields handed to the colour conversion).  IMAD.HI is avoided altogether: it costs far more than the
+// four FMA-pipe cycles its issue rate suggests (shift as multiply-high: 4 % slower than LEA.HI + IMAD.IADD).
 constexpr int kBias = 4096;
 constexpr int kRaw = 0x1080;
 __host__ __device__ constexpr uint32_t pk(int v) { return static_cast<uint32_t>(v) * 65537u; }  // v in both halves
@@ -680,23 +677,16 @@ __device__ __forceinline__ uint32_t fma_sub_from(uint32_t a, uint32_t b) {  // b
   asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
-// x >> (32 - log2 k) as a multiply-high.  ptxas keeps the 2^30 one (the /4 quotient) on the FMA pipe as
-// IMAD.HI and folds the 2^31 one (the /2 quotient) with the add that follows it into one LEA.HI.  Forcing
-// that one onto the FMA pipe as well (multiplier hidden in the kernel parameters) was measured 6 % slower,
-// and so was the sign-bit shift (T >> 13) as a multiply-high (1 %): IMAD.HI is quarter rate and the
-// FMA-heavy pipe becomes the bound.  The /4 quotient as a plain shift, or the adds left to ptxas, are
-// 1-2 % slower the other way (ALU pipe).
 // Constants the kernel wants in registers / the constant bank (BatchParams::kc): as literals ptxas rematerialises
 // them with a MOV before every use, and VIADDMNMX takes one immediate only.
-//   r3 = ph(3), r1 = ph(1): round-toward-zero addends;  k31 = 2^31 (as a parameter it stays an IMAD.HI on the FMA
-//   pipe; as a literal ptxas folds the shift and the add after it into one ALU-pipe LEA.HI);
+//   r3 = ph(3), r1 = ph(1): round-toward-zero addends;
 //   cb / cb3 = ph(2) / ph(5), cr / cr3 = ph(-254) / ph(-251): dividend offsets for high-band operands of bias kBias / kRaw
-struct ShiftK { uint32_t k30, k31, r3, r1, cb, cb3, cr, cr3; };
+struct ShiftK { uint32_t r3, r1, cb, cb3, cr, cr3; };
 __host__ __device__ constexpr uint32_t ph(int v) { return (static_cast<uint32_t>(v) & 0xFFFFu) * 65537u; }  // per-half constant
 // Round-toward-zero correction of a packed dividend without a sign test: with T = t + B in each half (B a multiple
 // of the divisor k = R + 1, |t| < B) the value  max(T, min(T + R, B + R))  is T + R for t < 0 and has the same
 // floor(. / k) as T for t >= 0, so that floor(result / k) = trunc(t / k) + B / k.  Two packed 16-bit min/max
-// instructions (VIADDMNMX.S16x2 + VIMNMX.S16x2) replace the shift + mask + multiply-add of the sign-bit form.
+// instructions (VIADDMNMX.S16x2 + VIMNMX.S16x2) replace the shift + mask + multiply-add of a sign-bit test.
 __device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
   uint32_t d;
   asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -713,11 +703,6 @@ template <int SH>
 __device__ __forceinline__ uint32_t shr_add(uint32_t a, uint32_t c) {
   uint32_t d;
   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(1u << (32 - SH)), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t k) {
-  uint32_t d;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(k));
   return d;
 }
 
@@ -1035,7 +1020,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   cp_async_wait_group<0>();
   __syncwarp();
   // r3 / r1 come from the kernel parameters: as literals ptxas rematerialises them with a MOV before every use
-  const ShiftK sk{1u << 30, 1u << 31, p.kc[0], p.kc[1], p.kc[3], p.kc[4], p.kc[5], p.kc[6]};
+  const ShiftK sk{p.kc[0], p.kc[1], p.kc[3], p.kc[4], p.kc[5], p.kc[6]};
   low_level_p<2>(w_s, lane, k10, sk);
   low_level_p<4>(w_s, lane, k10, sk);
   low_level_p<8>(w_s, lane, k10, sk);

@@ -24,27 +24,21 @@ constexpr int kTileSyms = kTile * kTile;
 
 // Packed decode-table entry (internal scratch format, 4 B instead of the reference's 6 B
 // AnsTableEntry, codec/decoder.cpp:20-24):
-//     bits 0..10   freq           (2048, the single-symbol table, is stored as 0)
-//     bits 11..18  symbol
-//     bits 19..31  bias' = (slot - cum_freq) - ((slot * freq) >> 11), signed
-// With F = freq << 21 (= entry << 21) the reference update
-//     state' = (state >> 11) * freq + slot - cum_freq          (ans/ans_decode.cl:38-41)
-// equals  umulhi(state, F) + bias'  exactly, because  state * freq = (state >> 11) * freq * 2048
-// + slot * freq  and  slot = state & 2047:  the decode loop needs one shift-free multiply-high
-// on the FMA pipe instead of three shifts and a mask on the ALU pipe.  A single-symbol table
-// (freq = 2048) decodes to that symbol whatever the state does, so F = 0 is harmless there.
+//     bits 0..11   freq                 (1..2048)
+//     bits 12..19  symbol
+//     bits 20..31  slot - cum_freq      (0..freq-1)
+// so that the reference update  state' = (state >> 11) * freq + slot - cum_freq  (ans/ans_decode.cl:38-41)
+// is SHF + LOP3 + SHF + IMAD.  (Round 1 used  umulhi(state, freq << 21) + bias'  -- one instruction less, all on
+// the FMA pipe -- but on sm_100 IMAD.HI costs far more than its four FMA-pipe cycles: the four-instruction
+// form is 2.3 % faster, profiles/README.md.)
 __host__ __device__ inline uint32_t pack_entry(uint32_t sym, uint32_t freq, uint32_t slot, uint32_t cum) {
-  const uint32_t f = freq & 0x7FFu;
-  const int32_t bias = static_cast<int32_t>(slot - cum) - static_cast<int32_t>((slot * f) >> 11);
-  return f | ((sym & 0xFFu) << 11) | (static_cast<uint32_t>(bias) << 19);
+  return (freq & 0xFFFu) | ((sym & 0xFFu) << 12) | (((slot - cum) & 0xFFFu) << 20);
 }
 // {symbol, freq, cum_freq} of slot `slot` back from a packed entry (table read-back API)
 __host__ __device__ inline void unpack_entry(uint32_t e, uint32_t slot, uint32_t *sym, uint32_t *freq, uint32_t *cum) {
-  const uint32_t f = e & 0x7FFu;
-  *sym = (e >> 11) & 0xFFu;
-  *freq = f ? f : 2048u;
-  const int32_t bias = (static_cast<int32_t>(e) >> 19) + static_cast<int32_t>((slot * f) >> 11);
-  *cum = slot - static_cast<uint32_t>(bias);
+  *sym = (e >> 12) & 0xFFu;
+  *freq = e & 0xFFFu;
+  *cum = slot - (e >> 20);
 }
 
 // Geometry + buffer description of one LoadCompressedDXTs-style call.  The compressed

@@ -389,12 +389,11 @@ class Decoder:
         t = self.download(d_t, n * kANSTableSize * 4).view(np.uint32).reshape(n, kANSTableSize)
         d_f.free()
         d_t.free()
-        # packed entry (csrc/gst_kernels.cuh): freq | sym << 11 | (slot - cum - ((slot * freq) >> 11)) << 19
+        # packed entry (csrc/gst_kernels.cuh): freq | sym << 12 | (slot - cum) << 20
         slot = np.arange(kANSTableSize, dtype=np.int64)[None, :]
-        f = (t & 0x7FF).astype(np.int64)
-        bias = (t.view(np.int32) >> 19).astype(np.int64) + ((slot * f) >> 11)
-        freq = np.where(f == 0, 2048, f)
-        return ((t >> 11) & 0xFF).astype(np.uint8), freq.astype(np.uint16), (slot - bias).astype(np.uint16)
+        freq = (t & 0xFFF).astype(np.uint16)
+        cum = slot - (t >> 20).astype(np.int64)
+        return ((t >> 12) & 0xFF).astype(np.uint8), freq, cum.astype(np.uint16)
 
 
 class FrameStreamer:

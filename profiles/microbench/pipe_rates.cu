@@ -75,6 +75,13 @@ BENCH_KERNEL(k_mix_imad_iadd, asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v
 BENCH_KERNEL(k_mix_lop_iadd_imad, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
 BENCH_KERNEL(k_isetp_only, { uint32_t t; asm volatile("{ .reg .pred p; setp.lt.u32 p, %1, %2; selp.u32 %0, %1, %2, p; }" : "=r"(t) : "r"(v[j]), "r"(c)); v[j] = t; })
 
+BENCH_KERNEL(k_imadhi_3iadd, asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(c)); asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k));)
+BENCH_KERNEL(k_imadhi_2lop, asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(c), "r"(k));)
+BENCH_KERNEL(k_imadhi_2imad, asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(k)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(c), "r"(k));)
+BENCH_KERNEL(k_imadwide, { unsigned long long w; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(v[j]), "r"(k), "l"((unsigned long long)c)); v[j] = (uint32_t)w ^ (uint32_t)(w >> 32); })
+BENCH_KERNEL(k_imadwide_2lop, { unsigned long long w; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(v[j]), "r"(k), "l"((unsigned long long)c)); v[j] = (uint32_t)w + (uint32_t)(w >> 32); } asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(k), "r"(c));)
+BENCH_KERNEL(k_leahi_imad, asm volatile("{ .reg .u32 t; shr.u32 t, %0, 31; add.u32 %0, t, %1; }" : "+r"(v[j]) : "r"(k)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(k), "r"(c));)
+
 __global__ void __launch_bounds__(1024) k_lds(uint32_t *out, uint32_t seed) {
   __shared__ uint32_t tab[2048];
   for (int i = threadIdx.x; i < 2048; i += 1024) tab[i] = (i * 2654435761u + seed) & 2047;
@@ -120,7 +127,9 @@ int main() {
       {"LOP3+VIADDMNMX alternating", k_mix_lop_viaddmnmx, 2}, {"IMAD+VIADDMNMX alternating", k_mix_imad_viaddmnmx, 2},
       {"IADD+VIADDMNMX alternating", k_mix_iadd_viaddmnmx, 2}, {"LOP3+VIMNMX3 alternating", k_mix_lop_vimnmx3, 2},
       {"IADD3 (2 adds)", k_iadd3_only, 1}, {"SHR31+ADD (LEA.HI?)", k_lea_hi, 1}, {"LOP3+LEA alternating", k_mix_lop_lea, 2},
-      {"IMAD+IADD alternating", k_mix_imad_iadd, 2}, {"LOP3+IADD+IMAD", k_mix_lop_iadd_imad, 3}, {"SETP+SELP", k_isetp_only, 2}};
+      {"IMAD+IADD alternating", k_mix_imad_iadd, 2}, {"LOP3+IADD+IMAD", k_mix_lop_iadd_imad, 3}, {"SETP+SELP", k_isetp_only, 2},
+      {"IMAD.HI+3xIADD", k_imadhi_3iadd, 4}, {"IMAD.HI+2xLOP3", k_imadhi_2lop, 3}, {"IMAD.HI+2xIMAD", k_imadhi_2imad, 3},
+      {"IMAD.WIDE (+LOP3)", k_imadwide, 2}, {"IMAD.WIDE+IADD+LOP3", k_imadwide_2lop, 3}, {"LEA.HI+IMAD alternating", k_leahi_imad, 2}};
   printf("device %s, %d SMs, clock attr %d kHz\n", prop.name, sms, khz);
   printf("%-34s %12s %16s\n", "instruction", "ms", "thread-ops/clk/SM");
   for (auto &e : ks) {
