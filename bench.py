@@ -5,8 +5,9 @@ compressed GB/s per B200 and at 2/4/8 GPUs, against the HBM roofline).
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU decode
 
-A step is one LoadCompressedDXTs-style call over the whole workload (default: BASELINE.json
-configs[3], a batch of 1024 2048x2048 textures per GPU; --config picks another).  Inputs
+A step is one LoadCompressedDXTs-style call over the workload (default: BASELINE.json configs[3],
+a batch of 1024 2048x2048 textures; --config picks another).  With N GPUs the batch is sharded,
+image i to rank i mod N (--scaling weak: every rank decodes the whole batch instead).  Inputs
 are reference-encoded .gst streams of seeded synthetic images (`--distinct` different images,
 tiled to the batch size); they are resident in HBM when the timed region starts.  The `e2e`
 figure runs the same workload through gst_decompress_host_batch with pinned HOST buffers:
@@ -56,9 +57,9 @@ def parse_args():
     ap.add_argument("--page", type=int, default=32, help="images per page on the e2e path")
     ap.add_argument("--depth", type=int, default=4, help="frames in flight of the configs[4] frame streamer")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
-    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
-                    help="weak: every GPU decodes the whole configured batch; strong: the batch is sharded, "
-                         "image i to rank i mod N")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="strong",
+                    help="strong (default): the configured batch is the job, image / frame i goes to rank i mod N; "
+                         "weak: every GPU decodes the whole configured batch")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample")
@@ -193,7 +194,7 @@ def run_reference(args, rank, world, cfg):
     line = {
         "impl": "reference", "metric": "decoded GTexel/s (.gst -> DXT1)", "value": val, "unit": "GTexel/s",
         "compressed_gb_s": cmp_bytes / total / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8/i32", "data": "synthetic",
         "config": {"workload": name, "width": width, "height": height,
                    "note": "CPU decode of a bounded sample per step, host memory only"},
@@ -210,11 +211,11 @@ def main():
     rank, local_rank, world = dist_env()
     cfg = CONFIGS[args.config]
     if args.images:
-        cfg = (cfg[0], cfg[1], args.images, cfg[3] + f" (images per GPU overridden to {args.images})")
+        cfg = (cfg[0], cfg[1], args.images, cfg[3] + f" (images overridden to {args.images})")
     if args.impl == "reference":
         run_reference(args, rank, world, cfg)
         return
-    width, height, images, name = cfg
+    width, height, images_total, name = cfg
 
     import torch
     import torch.distributed as dist
@@ -230,47 +231,66 @@ def main():
     from gst_b200.shard import reduce_job, shard_indices
 
     dec = gst_b200.Decoder(local_rank)
-    distinct = min(args.distinct, images)
+    distinct = min(args.distinct, images_total)
     files, goldens = load_streams(args.config, width, height, distinct, rank, world)
-    if args.scaling == "strong" and world > 1:
-        order = [i % distinct for i in shard_indices(images, rank, world)]  # image i -> rank i mod N
-        images = len(order)
-    else:
-        order = [(i + rank) % distinct for i in range(images)]  # ranks start at different images
+    # The job is the configured batch (BASELINE.json: "sharded across 1/2/4/8 B200", frames "streamed across 8 B200"):
+    # image / frame i goes to rank i mod N, no data-path collective.  --scaling weak makes every
+    # rank decode the whole configured batch instead (N independent replicas).
+    strong = args.scaling == "strong"
+    order = [i % distinct for i in (shard_indices(images_total, rank, world) if strong else range(images_total))]
+    if not strong:
+        order = [(j + rank) % distinct for j in order]  # replicas start at different images
+    images = len(order)
+    assert images > 0, f"rank {rank} has no image: {images_total} images over {world} ranks"
     batch = [files[j] for j in order]
-
-    # ---- device-resident inputs ---------------------------------------------------------
-    packed, hdrs = gst_b200.pack_batch(batch)
-    N = hdrs[0].num_blocks
-    d_cmp, d_out = dec.malloc(packed.size), dec.malloc(8 * N * images)
-    dec.upload(d_cmp, packed)
+    N = fx.header_of(files[0])["width"] * fx.header_of(files[0])["height"] // 16
     stream = dec.GetDefaultCommandQueue()
-    harr = (gst_b200.capi.gst_header * images)(*[h.to_c() for h in hdrs])
 
-    def step():
-        check(lib().gst_load_dxt_batch(dec.ctx, harr, images, stream, d_cmp.ptr, d_cmp.nbytes, d_out.ptr, None, 0, None))
+    class Resident:
+        """One batch packed in the LoadCompressedDXTs layout, resident in HBM, and the call that decodes it."""
+
+        def __init__(self, blobs):
+            self.n = len(blobs)
+            self.packed, self.hdrs = gst_b200.pack_batch(blobs)
+            self.d_cmp, self.d_out = dec.malloc(self.packed.size), dec.malloc(8 * N * self.n)
+            dec.upload(self.d_cmp, self.packed)
+            self.harr = (gst_b200.capi.gst_header * self.n)(*[h.to_c() for h in self.hdrs])
+            self.launches = lib().gst_launches_for_batch(self.harr, self.n)
+
+        def step(self):
+            check(lib().gst_load_dxt_batch(dec.ctx, self.harr, self.n, stream, self.d_cmp.ptr, self.d_cmp.nbytes,
+                                           self.d_out.ptr, None, 0, None))
+
+        def free(self):
+            self.d_cmp.free()
+            self.d_out.free()
+
+    res = Resident(batch)
+    step = res.step
 
     # ---- parity before timing: every distinct image against the CPU oracle ----------------
-    dec.memset(d_out, 0xEE)
+    dec.memset(res.d_out, 0xEE)
     step()
     dec.sync(stream)
     checked = 0
     for pos in range(min(distinct, images)):
-        got = dec.download(d_out, 8 * N, offset=pos * 8 * N)
+        got = dec.download(res.d_out, 8 * N, offset=pos * 8 * N)
         j = order[pos]
         if pos < 2:
             want = fx.oracle_decode(files[j], taps=False)["out"]
             assert np.array_equal(got, want), f"image {pos}: CUDA output differs from the CPU oracle"
         assert fx.matches_golden(got, goldens[j]), f"image {pos}: CUDA output differs from the encoder's PhysicalBlocks()"
         checked += 1
-    last = dec.download(d_out, 8 * N, offset=(images - 1) * 8 * N)
+    last = dec.download(res.d_out, 8 * N, offset=(images - 1) * 8 * N)
     assert fx.matches_golden(last, goldens[order[-1]]), "last image of the batch differs"
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step()
-    dec.sync(stream)
+    texels_rank = float(width) * height * images
+    cmp_rank = float(sum(f.size - 28 for f in batch))
+    alg_bytes_rank = cmp_rank + 8.0 * N * images  # SURVEY.md 8(d): (file - 28) + W*H/2 per image
+    # L2: when one step's inputs + outputs do not exceed twice the 126 MB L2, a 256 MB buffer is overwritten between
+    # the timed steps (outside the per-step events), so that no step finds its inputs in the cache
+    flush = alg_bytes_rank <= 2 * 126e6
+    d_flush = dec.malloc(256 << 20) if flush else None
 
     def barrier():
         if world > 1:
@@ -278,31 +298,71 @@ def main():
         torch.cuda.synchronize()
         dec.sync()
 
-    # ---- timed region: K steps, CUDA events on the launching stream -----------------------
-    dec.profile(True)
-    barrier()
-    ev0 = dec.record(stream)
-    marks = [ev0]
-    for _ in range(args.steps):
+    def timed(run_step, steps):
+        """-> (total device ms of `steps` steps, sorted per-step ms); CUDA events on the launching stream."""
+        barrier()
+        if not flush:
+            marks = [dec.record(stream)]
+            for _ in range(steps):
+                run_step()
+                marks.append(dec.record(stream))  # one event per step: median and best step (SURVEY.md 8d)
+            marks[-1].wait()
+            per = [marks[i].elapsed_ms(marks[i + 1]) for i in range(steps)]
+            total = marks[0].elapsed_ms(marks[-1])
+        else:
+            pairs = []
+            for _ in range(steps):
+                dec.memset(d_flush, 0x5A)
+                a = dec.record(stream)
+                run_step()
+                pairs.append((a, dec.record(stream)))
+            pairs[-1][1].wait()
+            per = [a.elapsed_ms(b) for a, b in pairs]
+            total = float(sum(per))
+        barrier()
+        return total, sorted(per)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
-        marks.append(dec.record(stream))  # one event per step: median and best step
-    ev1 = marks[-1]
-    ev1.wait()
-    barrier()
-    dec.profile(False)
-    ms_total = ev0.elapsed_ms(ev1)
-    per_step = sorted(marks[i].elapsed_ms(marks[i + 1]) for i in range(args.steps))
-    kernel_ms, calls = dec.profile_read()
-    texels_rank = float(width) * height * images
-    cmp_rank = float(sum(f.size - 28 for f in batch))
-    alg_bytes_rank = cmp_rank + 8.0 * N * images  # (file - 28) + W*H/2 per image
+    dec.sync(stream)
+
+    # ---- timed region: K steps, the production path (no per-kernel events) ----------------------
+    ms_total, per_step = timed(step, args.steps)
     # whole job: max over ranks of the device time, sum over ranks of the units processed
-    ms_total, (texels_job, cmp_job, h2d_job, d2h_job) = reduce_job(
-        ms_total, [texels_rank, cmp_rank, float(packed.size), 8.0 * N * images])
+    ms_total, (texels_job, cmp_job, h2d_job, d2h_job, alg_job) = reduce_job(
+        ms_total, [texels_rank, cmp_rank, float(res.packed.size), 8.0 * N * images, alg_bytes_rank])
     ms_step = ms_total / args.steps
+
+    # ---- per-kernel times: a separate short pass with events around every kernel -----------------
+    dec.profile(True)
+    prof_steps = min(args.steps, 5)
+    timed(step, prof_steps)
+    dec.profile(False)
+    kernel_ms, calls = dec.profile_read()
+    per_call = {k: v / max(calls, 1) for k, v in kernel_ms.items()}
+
+    # ---- the other scaling mode, for the record (N > 1 only) --------------------------------------
+    other = None
+    if world > 1:
+        o_order = ([(i + rank) % distinct for i in range(images_total)] if strong
+                   else [i % distinct for i in shard_indices(images_total, rank, world)])
+        if o_order:
+            o_res = Resident([files[j] for j in o_order])
+            for _ in range(3):
+                o_res.step()
+            o_ms, _ = timed(o_res.step, max(3, args.steps // 2))
+            o_ms, (o_tex,) = reduce_job(o_ms, [float(width) * height * len(o_order)])
+            o_step = o_ms / max(3, args.steps // 2)
+            other = {"scaling": "weak" if strong else "strong", "images_per_gpu": len(o_order), "ms_per_step": o_step,
+                     "value": o_tex / (o_step * 1e-3) / 1e9, "unit": "GTexel/s"}
+            o_res.free()
 
     # ---- end to end: host .gst buffers -> host DXT1 blocks ---------------------------------
     e2e = None
+    e2e_steps = args.e2e_steps or max(1, min(args.steps, 10))
     if not args.no_e2e:
         pin_files = []
         for f in files:
@@ -319,22 +379,21 @@ def main():
             if streamer is None:
                 check(lib().gst_decompress_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, pin_out.ptr, pin_out.nbytes))
                 return
-            # configs[4]: the demo player loop (demo/demo.cpp:145-243) with `depth` frames in flight; every
-            # frame is copied back to the host as soon as it is decoded
+            # configs[4]: the demo player loop (demo/demo.cpp:145-243) with `depth` frames in flight: every frame is
+            # uploaded from where it lies, decoded and copied back to the host on its slot's stream; a frame is
+            # waited for `depth - 1` submissions after its own
             tickets = []
             for f in range(images):
-                tickets.append(streamer.submit(pin_files[order[f]]))
+                tickets.append(streamer.submit(pin_files[order[f]], host_out=pin_out.ptr + f * 8 * N, direct=True))
                 if f >= args.depth - 1:
-                    k = f - (args.depth - 1)
-                    check(lib().gst_download_async(dec.ctx, stream, pin_out.ptr + k * 8 * N, streamer.wait(tickets[k]), 8 * N))
+                    streamer.wait(tickets[f - (args.depth - 1)])
             for k in range(max(0, images - (args.depth - 1)), images):
-                check(lib().gst_download_async(dec.ctx, stream, pin_out.ptr + k * 8 * N, streamer.wait(tickets[k]), 8 * N))
-            dec.sync(stream)
+                streamer.wait(tickets[k])
 
+        pin_out.array[:] = 0xEE
         e2e_step()  # warm-up: grows the staging buffers
-        assert fx.matches_golden(pin_out.array[: 8 * N], goldens[order[0]]), "e2e output differs"
-        assert fx.matches_golden(pin_out.array[(images - 1) * 8 * N:], goldens[order[-1]]), "e2e output differs"
-        e2e_steps = args.e2e_steps or max(1, min(args.steps, 10))
+        for pos in sorted({0, images // 3, images // 2, (2 * images) // 3, images - 1}):  # frames / images across the step
+            assert fx.matches_golden(pin_out.array[pos * 8 * N:(pos + 1) * 8 * N], goldens[order[pos]]), f"e2e output {pos} differs"
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -346,9 +405,11 @@ def main():
                "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(d2h_job),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
-               "api": "gst_streamer_submit/wait per frame" if streamer is not None else "gst_decompress_host_batch",
+               "api": "gst_streamer_submit_ex (direct upload, read-back on the slot's stream) + gst_streamer_wait per frame"
+                      if streamer is not None else "gst_decompress_host_batch",
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
         if streamer is not None:
+            e2e["frames_per_s"] = images_total * e2e_steps / dt
             streamer.close()
     # ---- photos_sf shape: host .gst buffers -> textures resident in device memory ---------------
     e2e_res = None
@@ -356,17 +417,17 @@ def main():
         probe = dec.pinned(16 * images)
 
         def res_step():
-            check(lib().gst_load_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, d_out.ptr, d_out.nbytes))
+            check(lib().gst_load_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, res.d_out.ptr, res.d_out.nbytes))
             # the step's result read: first and last block of every image (strided D2H)
-            dec.download_2d(probe, d_out, 8, images, src_pitch=8 * N, dst_pitch=16)
-            dec.download_2d(probe, d_out, 8, images, src_pitch=8 * N, dst_pitch=16, src_offset=8 * N - 8, dst_offset=8)
+            dec.download_2d(probe, res.d_out, 8, images, src_pitch=8 * N, dst_pitch=16)
+            dec.download_2d(probe, res.d_out, 8, images, src_pitch=8 * N, dst_pitch=16, src_offset=8 * N - 8, dst_offset=8)
 
-        dec.memset(d_out, 0xEE)
+        dec.memset(res.d_out, 0xEE)
         res_step()
         dec.sync()
-        got0 = dec.download(d_out, 8 * N, offset=0)
+        got0 = dec.download(res.d_out, 8 * N, offset=0)
         assert fx.matches_golden(got0, goldens[order[0]]), "resident e2e output differs"
-        gotl = dec.download(d_out, 8 * N, offset=(images - 1) * 8 * N)
+        gotl = dec.download(res.d_out, 8 * N, offset=(images - 1) * 8 * N)
         assert fx.matches_golden(gotl, goldens[order[-1]]), "resident e2e output differs"
         assert np.array_equal(probe.array[:8], got0[:8]) and np.array_equal(probe.array[-8:], gotl[-8:])
         barrier()
@@ -377,7 +438,7 @@ def main():
         dt = time.perf_counter() - t0
         dt, _ = reduce_job(dt, [])
         e2e_res = {"value": texels_job * e2e_steps / dt / 1e9, "unit": "GTexel/s",
-                   "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(16 * images * world),
+                   "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(16 * images_total if strong else 16 * images * world),
                    "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                    "note": "host .gst -> DXT1 resident in device memory (LoadCompressedDXTs into a device buffer); "
                            "16-byte probe per image read back"}
@@ -404,48 +465,51 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak, peak_src = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        # Algorithmic bytes (compressed bytes read once + DXT1 bytes written once) split
-        # over the two heavy kernels: rans_streams reads every compressed stream and frequency table,
-        # wavelet_assemble writes every DXT1 block.  The transposed symbol scratch between them is
-        # an intermediate and not counted.  `roofline` describes whichever kernel takes longer.
-        per_call = {k: v / max(calls, 1) for k, v in kernel_ms.items()}
+        peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        # the roofline figure is the STEP: algorithmic bytes (compressed bytes read once + DXT1 bytes
+        # written once, intermediates not counted) of this rank over its step time, against the measured HBM copy
+        # bandwidth.  Per kernel: rans_streams reads every compressed stream and frequency table, wavelet_assemble
+        # writes every DXT1 block.
         alg = {"rans_streams": cmp_rank, "wavelet_assemble": 8.0 * N * images}
-        dom = max(alg, key=lambda k: per_call.get(k, 0.0))
-        fused_bytes, fused_ms = alg[dom], per_call[dom]
-        achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
-        # DRAM bytes per launch of that kernel, from the committed `ncu --set full` capture
-        # (profiles/traffic.json holds dram__bytes_read + dram__bytes_write per image of a given size)
+        kernels = {}
+        for k, v in per_call.items():
+            kernels[k] = {"ms": v}
+            if k in alg and v > 0:
+                kernels[k].update(alg_bytes=alg[k], achieved=alg[k] / (v * 1e-3) / 1e9, frac=alg[k] / (v * 1e-3) / 1e9 / peak)
+        # DRAM bytes per step from the committed `ncu --set full` capture (profiles/traffic.json: dram__bytes_read +
+        # dram__bytes_write per image of a given size, per kernel)
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            per_img = tj.get(f"{width}x{height}", {}).get(dom)
-            if per_img is not None:
-                traffic = float(per_img) * images
+            per_img = tj.get(f"{width}x{height}")
+            if per_img:
+                traffic = float(sum(v for k, v in per_img.items() if isinstance(v, (int, float)))) * images
         except Exception:
             pass
-        step_gbs = alg_bytes_rank / (ms_step * 1e-3) / 1e9
+        step_rank_ms = per_step[len(per_step) // 2]
+        step_gbs = alg_job / (ms_step * 1e-3) / 1e9 / world  # per GPU
         line = {
             "metric": "decoded GTexel/s (.gst -> DXT1)", "value": texels_job / (ms_step * 1e-3) / 1e9,
             "unit": "GTexel/s", "compressed_gb_s": cmp_job / (ms_step * 1e-3) / 1e9,
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "ms_per_step_median_rank0": per_step[len(per_step) // 2], "ms_per_step_best_rank0": per_step[0],
-            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
+            "ms_per_step_median_rank0": step_rank_ms, "ms_per_step_best_rank0": per_step[0],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8/i32 (integer only)",
             "data": "synthetic",
-            "config": {"workload": name, "width": width, "height": height, "images_per_gpu": images,
-                       "distinct_images": distinct, "bits_per_texel": 8.0 * cmp_rank / texels_rank,
-                       "sharding": "independent images per rank, no data-path collective",
-                       "l2": "inputs+outputs per step exceed the 126 MB L2" if alg_bytes_rank > 2 * 126e6 else
-                             "working set fits L2 (latency-bound config)",
+            "config": {"workload": name, "width": width, "height": height, "images": images_total if strong else images * world,
+                       "images_per_gpu": images, "distinct_images": distinct,
+                       "bits_per_texel": 8.0 * cmp_rank / texels_rank,
+                       "sharding": ("image i -> rank i mod N" if strong else "every rank decodes the whole batch") +
+                                   ", no data-path collective",
+                       "l2": "a 256 MB buffer is overwritten between timed steps (working set fits the 126 MB L2)" if flush
+                             else "inputs + outputs per step exceed twice the 126 MB L2, no flush",
                        "parity": f"{checked} distinct images + last checked bit-exact before timing"},
-            "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                         "kernel_ms": fused_ms, "kernel_bytes": fused_bytes,
-                         "step_achieved": step_gbs, "step_frac": step_gbs / peak,
-                         "kernel_ms_all": per_call,
-                         "kernel_alg_bytes": alg},
-            "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": lib().gst_launches_per_batch() * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "step (build_tables + rans_streams + wavelet_assemble)",
+                         "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                         "peak_source": peak_src, "traffic": traffic, "alg_bytes_per_step_per_gpu": alg_job / world,
+                         "kernels": kernels},
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "other_scaling": other,
+            "gpu_launches": res.launches * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

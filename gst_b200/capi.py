@@ -58,6 +58,7 @@ PROTOTYPES = {
     "gst_load_host_batch": (_int, [_vp, _pp, C.POINTER(_sz), _u32, _u32, _int, _vp, _sz]),
     "gst_streamer_create": (_int, [_vp, _u32, _u32, _u32, _int, C.POINTER(_vp)]),
     "gst_streamer_submit": (_int, [_vp, _vp, _sz, _vp, C.POINTER(C.c_uint64)]),
+    "gst_streamer_submit_ex": (_int, [_vp, _vp, _sz, _vp, _vp, _u32, C.POINTER(C.c_uint64)]),
     "gst_streamer_wait": (_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "gst_streamer_destroy": (None, [_vp]),
     "gst_load_dxt_batch_tapped": (_int, [_vp, _hdr_p, _u32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
@@ -71,6 +72,7 @@ PROTOTYPES = {
     "gst_ans_encode_stream": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "gst_build_tables": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "gst_launches_per_batch": (_int, []),
+    "gst_launches_for_batch": (_int, [_hdr_p, _u32]),
     "gst_profile_enable": (_int, [_vp, _int]),
     "gst_profile_read": (_int, [_vp, C.POINTER(C.c_double), _u32, C.POINTER(C.c_uint64)]),
 }

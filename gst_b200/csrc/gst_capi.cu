@@ -6,15 +6,18 @@
 // CUDA stream instead of the reference's explicit cl_event DAG on out-of-order queues.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gst_cuda.h"
@@ -61,14 +64,34 @@ struct gst_ctx {
   uint8_t *arena = nullptr;
   size_t arena_size = 0;
   size_t arena_off = 0;
-  // staging of gst_decompress_host_batch, one slot per work stream, grow-only
-  std::mutex host_batch_mutex;
+  // Scratch of calls made without a preallocated arena: one grow-only buffer per stream the context has seen.
+  // Calls on one stream are ordered, so the buffer is reused by the next call without any allocation; it is
+  // released with the context (or gst_free_scratch).
+  struct StreamScratch {
+    std::mutex m;  // held from the lookup to the last launch of a call: a concurrent call on the same stream must not
+                   // regrow the buffer in between
+    uint8_t *ptr = nullptr;
+    size_t cap = 0;
+  };
+  std::mutex scratch_mutex;
+  std::unordered_map<cudaStream_t, std::unique_ptr<StreamScratch>> stream_scratch;
+  // staging of gst_decompress_host_batch / gst_load_host_batch: a pool of slots (pinned staging x 2, device input,
+  // device output, stream), grow-only.  A worker thread of a call takes a free slot for the pages it handles, so
+  // concurrent callers (the reference's pool threads, demo/photos_sf.cpp:747-830) overlap instead of queueing
+  // behind one another.
+  std::mutex slot_mutex;
+  std::condition_variable slot_cv;
+  bool slot_busy[kHostSlots] = {};
   struct HostSlotT {
     uint8_t *pinned[2] = {nullptr, nullptr};
     cudaEvent_t h2d_done[2] = {nullptr, nullptr};
     uint8_t *d_in = nullptr, *d_out = nullptr;
     size_t cap_in = 0, cap_out = 0;
   } host_slots[kHostSlots];
+  // workspace of the standalone rANS decode / encode entry points (grow-only, one call at a time)
+  std::mutex ans_mutex;
+  uint8_t *ans_ws = nullptr;
+  size_t ans_ws_cap = 0;
   // optional per-kernel timing (gst_profile_*): events around every kernel of every call
   std::mutex prof_mutex;
   bool prof_on = false;
@@ -119,7 +142,7 @@ struct DeviceGuard {
   }
 };
 
-int check_header(const gst_header &h) {
+int check_dims(const gst_header &h) {
   if (h.width == 0 || h.height == 0 || (h.width % 128) || (h.height % 128))
     return fail(GST_ERR_INVALID, "image dimensions %ux%u must be non-zero multiples of 128", h.width, h.height);
   const uint64_t n = static_cast<uint64_t>(h.width / 4) * (h.height / 4);
@@ -130,6 +153,20 @@ int check_header(const gst_header &h) {
   if ((h.y_cmp_sz | h.chroma_cmp_sz | h.palette_sz | h.indices_sz) & 3u)
     return fail(GST_ERR_INVALID, "compressed stream sizes must be multiples of 4");
   if (n > 0x7FFFFFFFull / 8) return fail(GST_ERR_INVALID, "image too large");
+  return GST_OK;
+}
+
+int check_header(const gst_header &h) {
+  int rc = check_dims(h);
+  if (rc) return rc;
+  const uint64_t n = static_cast<uint64_t>(h.width / 4) * (h.height / 4);
+  // every stream starts with one u32 end offset per group and every group ends with its 32 states
+  const uint64_t groups[4] = {2 * n / gst::kGroupSyms, 4 * n / gst::kGroupSyms, h.palette_bytes / gst::kGroupSyms,
+                              n / gst::kGroupSyms};
+  const uint32_t sizes[4] = {h.y_cmp_sz, h.chroma_cmp_sz, h.palette_sz, h.indices_sz};
+  for (int s = 0; s < 4; ++s)
+    if (sizes[s] < groups[s] * (4 + 4 * gst::kLanes))
+      return fail(GST_ERR_INVALID, "stream %d of %u bytes cannot hold %llu groups", s, sizes[s], (unsigned long long)groups[s]);
   return GST_OK;
 }
 
@@ -186,9 +223,11 @@ struct Taps {
   void *symbols = nullptr, *planes = nullptr, *indices = nullptr;
 };
 
+// inline_offsets: n == 1 and cmp_dev holds NO offset table (its first off_region bytes are not read): the eight
+// offsets travel in the kernel parameters (the frame streamer uploads a file as it lies)
 int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t stream, const void *cmp_dev,
                  size_t cmp_bytes, void *out_dev, int rgb, const Taps &taps, void *const *wait_events,
-                 uint32_t n_wait, void **done_event) {
+                 uint32_t n_wait, void **done_event, bool inline_offsets = false) {
   if (!ctx) return fail(GST_ERR_INVALID, "null context");
   if (!cmp_dev || !out_dev) return fail(GST_ERR_INVALID, "null device buffer");
   BatchLayout L;
@@ -200,7 +239,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   for (uint32_t i = 0; i < n_wait; ++i)
     GST_CUDA_TRY(cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(wait_events[i]), 0));
 
-  // scratch: preallocated arena (bump, never reset) or a stream-ordered allocation
+  // scratch: preallocated arena (bump, never reset), or the grow-only buffer this stream's calls share
   uint8_t *scratch = nullptr;
   bool from_arena = false;
   {
@@ -214,7 +253,29 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
       from_arena = true;
     }
   }
-  if (!from_arena) GST_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), L.scratch_bytes, stream));
+  std::unique_lock<std::mutex> scratch_lock;
+  if (!from_arena) {
+    gst_ctx::StreamScratch *ssp = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(ctx->scratch_mutex);
+      std::unique_ptr<gst_ctx::StreamScratch> &slot = ctx->stream_scratch[stream];
+      if (!slot) slot.reset(new gst_ctx::StreamScratch);
+      ssp = slot.get();
+    }
+    scratch_lock = std::unique_lock<std::mutex>(ssp->m);
+    gst_ctx::StreamScratch &ss = *ssp;
+    if (ss.cap < L.scratch_bytes) {
+      // stream-ordered: the old buffer is released after the work already queued on this stream
+      if (ss.ptr) GST_CUDA_TRY(cudaFreeAsync(ss.ptr, stream));
+      ss.ptr = nullptr;
+      ss.cap = 0;
+      const size_t cap = align_up(L.scratch_bytes + L.scratch_bytes / 8, 1 << 20);
+      cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ss.ptr), cap, stream);
+      if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "scratch allocation of %zu bytes failed: %s", cap, cudaGetErrorString(e));
+      ss.cap = cap;
+    }
+    scratch = ss.ptr;
+  }
 
   gst::BatchParams p{};
   p.cmp = static_cast<const uint8_t *>(cmp_dev);
@@ -235,6 +296,20 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
   gst::fill_kernel_constants(&p);
+  if (inline_offsets) {
+    if (n != 1) return fail(GST_ERR_INVALID, "inline offsets need a single image");
+    const uint32_t N = L.n_blocks;
+    const uint32_t out_sz[4] = {2 * N, 4 * N, hdrs[0].palette_bytes, N};
+    const uint32_t in_sz[4] = {hdrs[0].y_cmp_sz, hdrs[0].chroma_cmp_sz, hdrs[0].palette_sz, hdrs[0].indices_sz};
+    uint32_t oa = 0, ia = 0;
+    for (int k = 0; k < 4; ++k) {
+      p.off8[k] = oa;
+      p.off8[4 + k] = ia;
+      oa += out_sz[k];
+      ia += in_sz[k];
+    }
+    p.inline_off = 1;
+  }
   p.tap_symbols = static_cast<uint8_t *>(taps.symbols);
   p.tap_planes = static_cast<int8_t *>(taps.planes);
   p.tap_indices = static_cast<int32_t *>(taps.indices);
@@ -245,16 +320,16 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
     std::lock_guard<std::mutex> lock(ctx->prof_mutex);
     profiled = ctx->prof_on;
   }
+  if (profiled) {
+    std::lock_guard<std::mutex> lock(ctx->prof_mutex);
+    profiled = ctx->prof_events.size() < 4096 * (gst::kLaunchesPerBatch + 1);  // unread records are capped
+  }
   if (profiled)
     for (auto &m : marks) GST_CUDA_TRY(cudaEventCreateWithFlags(&m, cudaEventDefault));
   cudaError_t e = gst::launch_decode_batch(p, rgb, L.max_palette, stream, profiled ? marks : nullptr);
   if (profiled) {
     std::lock_guard<std::mutex> lock(ctx->prof_mutex);
     ctx->prof_events.insert(ctx->prof_events.end(), marks, marks + gst::kLaunchesPerBatch + 1);
-  }
-  if (!from_arena) {
-    cudaError_t e2 = cudaFreeAsync(scratch, stream);
-    if (e == cudaSuccess) e = e2;
   }
   if (e != cudaSuccess) return fail(GST_ERR_CUDA, "decode launch failed: %s", cudaGetErrorString(e));
   if (done_event) {
@@ -382,6 +457,9 @@ void gst_ctx_destroy(gst_ctx *ctx) {
       cudaStreamDestroy(s);
     }
   if (ctx->arena) cudaFree(ctx->arena);
+  for (auto &kv : ctx->stream_scratch)
+    if (kv.second && kv.second->ptr) cudaFree(kv.second->ptr);
+  if (ctx->ans_ws) cudaFree(ctx->ans_ws);
   for (auto &hs : ctx->host_slots) {
     for (int k = 0; k < 2; ++k) {
       if (hs.pinned[k]) cudaFreeHost(hs.pinned[k]);
@@ -516,14 +594,6 @@ int gst_parse_header(const uint8_t *gst, size_t len, gst_header *hdr) {
   const uint64_t need = static_cast<uint64_t>(GST_HEADER_BYTES) + 2048 + hdr->y_cmp_sz + hdr->chroma_cmp_sz +
                         hdr->palette_sz + hdr->indices_sz;
   if (need > len) return fail(GST_ERR_INVALID, "header describes %llu bytes but the file has %zu", (unsigned long long)need, len);
-  // every stream starts with one u32 end offset per group
-  const uint64_t n = static_cast<uint64_t>(hdr->width / 4) * (hdr->height / 4);
-  const uint64_t groups[4] = {2 * n / gst::kGroupSyms, 4 * n / gst::kGroupSyms, hdr->palette_bytes / gst::kGroupSyms,
-                              n / gst::kGroupSyms};
-  const uint32_t sizes[4] = {hdr->y_cmp_sz, hdr->chroma_cmp_sz, hdr->palette_sz, hdr->indices_sz};
-  for (int s = 0; s < 4; ++s)
-    if (sizes[s] < groups[s] * (4 + 4 * gst::kLanes))
-      return fail(GST_ERR_INVALID, "stream %d of %u bytes cannot hold %llu groups", s, sizes[s], (unsigned long long)groups[s]);
   return GST_OK;
 }
 
@@ -612,6 +682,12 @@ int gst_free_scratch(gst_ctx *ctx) {
   if (!ctx) return fail(GST_ERR_INVALID, "null context");
   DeviceGuard guard(ctx->device);
   GST_CUDA_TRY(cudaDeviceSynchronize());
+  {
+    std::lock_guard<std::mutex> lock(ctx->scratch_mutex);
+    for (auto &kv : ctx->stream_scratch)
+      if (kv.second && kv.second->ptr) cudaFree(kv.second->ptr);
+    ctx->stream_scratch.clear();
+  }
   std::lock_guard<std::mutex> lock(ctx->arena_mutex);
   if (ctx->arena) GST_CUDA_TRY(cudaFree(ctx->arena));
   ctx->arena = nullptr;
@@ -673,7 +749,6 @@ int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens
   const size_t per_image = mode ? static_cast<size_t>(h0.width) * h0.height * 3 : static_cast<size_t>(h0.width) * h0.height / 2;
   if (out_cap < per_image * n) return fail(GST_ERR_SMALL, "output needs %zu bytes, buffer has %zu", per_image * n, out_cap);
 
-  std::lock_guard<std::mutex> batch_lock(ctx->host_batch_mutex);
   const uint32_t n_pages = (n + page - 1) / page;
   // textures staying on the device: the host-side page packing is the bottleneck, use every worker; textures
   // coming back to the host: the D2H copies own the link and the host memory system, four workers are enough
@@ -684,8 +759,31 @@ int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens
 
   auto worker = [&](uint32_t si) {
     cudaSetDevice(ctx->device);
-    HostSlot &s = ctx->host_slots[si];
-    cudaStream_t stream = ctx->host_streams[si];
+    // take a free staging slot (and its stream) from the context's pool; give it back when this worker is done
+    uint32_t slot_id = 0;
+    {
+      std::unique_lock<std::mutex> lock(ctx->slot_mutex);
+      ctx->slot_cv.wait(lock, [&] {
+        for (uint32_t k = 0; k < kHostSlots; ++k)
+          if (!ctx->slot_busy[k]) return true;
+        return false;
+      });
+      while (ctx->slot_busy[slot_id]) ++slot_id;
+      ctx->slot_busy[slot_id] = true;
+    }
+    struct Release {
+      gst_ctx *ctx;
+      uint32_t id;
+      ~Release() {
+        {
+          std::lock_guard<std::mutex> lock(ctx->slot_mutex);
+          ctx->slot_busy[id] = false;
+        }
+        ctx->slot_cv.notify_one();
+      }
+    } release{ctx, slot_id};
+    HostSlot &s = ctx->host_slots[slot_id];
+    cudaStream_t stream = ctx->host_streams[slot_id];
     std::vector<gst_header> hdrs(page);
     auto bail = [&](int code, const char *what, cudaError_t e) {
       slot_rc[si] = code;
@@ -736,6 +834,17 @@ int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens
         slot_err[si] = g_err;
         return;
       }
+      // the output stride and the staging were sized from the first file of the call: every page must match it
+      // (inside a page pack_impl has already checked the images against each other)
+      if (hdrs[0].width != h0.width || hdrs[0].height != h0.height) {
+        slot_rc[si] = GST_ERR_INVALID;
+        char msg[160];
+        snprintf(msg, sizeof msg, "image %u is %ux%u but image 0 is %ux%u: one call needs equal dimensions", first,
+                 hdrs[0].width, hdrs[0].height, h0.width, h0.height);
+        slot_err[si] = msg;
+        cudaStreamSynchronize(stream);
+        return;
+      }
       e = cudaMemcpyAsync(s.d_in, s.pinned[j], L.total_cmp, cudaMemcpyHostToDevice, stream);
       if (e == cudaSuccess) e = cudaEventRecord(s.h2d_done[j], stream);
       if (e != cudaSuccess) return bail(GST_ERR_CUDA, "upload failed", e);
@@ -784,7 +893,7 @@ int gst_streamer_create(gst_ctx *ctx, uint32_t width, uint32_t height, uint32_t 
   gst_header h{};
   h.width = width;
   h.height = height;
-  int rc = check_header(h);
+  int rc = check_dims(h);
   if (rc) return rc;
   DeviceGuard guard(ctx->device);
   gst_streamer *st = new (std::nothrow) gst_streamer;
@@ -825,7 +934,12 @@ void gst_streamer_destroy(gst_streamer *st) {
   delete st;
 }
 
-int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, uint64_t *ticket) {
+namespace {
+// One frame: [512 unused bytes][file minus its 28-byte header] on the device -- the frequency tables and the four
+// streams lie in the file exactly as the decode kernels want them, and the eight offsets of a single image travel in
+// the kernel parameters, so nothing is packed.  direct: the copy reads the caller's buffer (which must stay valid,
+// and should be pinned, until the frame is waited for); otherwise the frame goes through the slot's pinned staging.
+int streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, void *out_host, uint64_t *ticket, bool direct) {
   if (!st || !gst) return fail(GST_ERR_INVALID, "null argument");
   gst_header h;
   int rc = gst_parse_header(gst, len, &h);
@@ -837,7 +951,8 @@ int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *
   gst_streamer::Slot &s = st->slots[t % st->depth];
   // the slot's previous frame (ticket t - depth) must have been decoded: its staging is reused
   if (s.ticket != UINT64_MAX) GST_CUDA_TRY(cudaEventSynchronize(s.done));
-  const size_t need = kQuantum + len;  // offsets region + everything after the header
+  const size_t body = len - GST_HEADER_BYTES;
+  const size_t need = kQuantum + body;
   if (need > s.cap_in) {
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.d_in) cudaFree(s.d_in);
@@ -846,21 +961,34 @@ int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *
     GST_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s.pinned), s.cap_in, cudaHostAllocDefault));
     GST_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in));
   }
-  const uint8_t *files[1] = {gst};
-  const size_t lens[1] = {len};
-  BatchLayout L;
-  rc = pack_impl(files, lens, 1, s.pinned, s.cap_in, &h, true, &L);  // demo/demo.cpp:165-192
-  if (rc) return rc;
-  GST_CUDA_TRY(cudaMemcpyAsync(s.d_in, s.pinned, L.total_cmp, cudaMemcpyHostToDevice, s.stream));
+  const uint8_t *src = gst + GST_HEADER_BYTES;
+  if (!direct) {
+    memcpy(s.pinned, src, body);
+    src = s.pinned;
+  }
+  GST_CUDA_TRY(cudaMemcpyAsync(s.d_in + kQuantum, src, body, cudaMemcpyHostToDevice, s.stream));  // demo/demo.cpp:189-192
   void *dst = out_dev ? out_dev : s.d_out;
-  rc = decode_batch(st->ctx, &h, 1, s.stream, s.d_in, s.cap_in, dst, st->mode, Taps{}, nullptr, 0, nullptr);
+  rc = decode_batch(st->ctx, &h, 1, s.stream, s.d_in, s.cap_in, dst, st->mode, Taps{}, nullptr, 0, nullptr, true);
   if (rc) return rc;
+  // read-back on the slot's own stream: the slot's next frame is ordered behind it, and `done` covers it
+  if (out_host) GST_CUDA_TRY(cudaMemcpyAsync(out_host, dst, st->frame_bytes, cudaMemcpyDeviceToHost, s.stream));
   GST_CUDA_TRY(cudaEventRecord(s.done, s.stream));
   s.ticket = t;
   s.frame_dev = dst;
   st->next_ticket = t + 1;
   if (ticket) *ticket = t;
   return GST_OK;
+}
+}  // namespace
+
+int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, uint64_t *ticket) {
+  return streamer_submit(st, gst, len, out_dev, nullptr, ticket, false);
+}
+
+int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, void *out_host,
+                           uint32_t flags, uint64_t *ticket) {
+  if (flags & ~static_cast<uint32_t>(GST_SUBMIT_DIRECT)) return fail(GST_ERR_INVALID, "unknown submit flags 0x%x", flags);
+  return streamer_submit(st, gst, len, out_dev, out_host, ticket, (flags & GST_SUBMIT_DIRECT) != 0);
 }
 
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev) {
@@ -1068,6 +1196,12 @@ void gst_ans_destroy(gst_ans_decoder *d) {
 }
 
 int gst_launches_per_batch(void) { return gst::kLaunchesPerBatch; }
+
+int gst_launches_for_batch(const gst_header *hdrs, uint32_t n) {
+  BatchLayout L;
+  if (layout_batch(hdrs, n, &L)) return 0;
+  return gst::is_small_call(n, L.groups_per_plane, L.max_palette) ? 2 : 3;
+}
 
 int gst_profile_enable(gst_ctx *ctx, int on) {
   if (!ctx) return fail(GST_ERR_INVALID, "null context");

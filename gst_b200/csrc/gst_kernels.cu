@@ -62,6 +62,11 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
 }
+// Programmatic dependent launch: the next kernel of the stream may be scheduled once every CTA of this one has
+// passed pdl_launch_dependents(); it blocks in pdl_wait() until this kernel has completed and its writes are visible.
+// Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lanemask_gt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
@@ -136,20 +141,15 @@ __device__ __forceinline__ void cp_async_wait_group() {
 // emit(m, acc): called 16 times; acc holds the 16 symbols at positions q0 = 240 - 16m .. q0 + 15 of
 // this lane's 256-symbol run of every chain:
 //   ILV = false: acc[4c + j] = symbols q0 + 4j .. q0 + 4j + 3 of chain c, little-endian packed
-//   ILV = true (NC even): chains 2i and 2i + 1 byte-interleaved, acc[8i + j] = {chain 2i @ q0 + 2j, chain 2i+1 @ q0 + 2j,
-//                chain 2i @ q0 + 2j + 1, chain 2i+1 @ q0 + 2j + 1} -- the layout wavelet_assemble_kernel
+//   ILV = true (NC = 2): the two chains byte-interleaved, acc[j] = {chain 0 @ q0 + 2j, chain 1 @ q0 + 2j,
+//                chain 0 @ q0 + 2j + 1, chain 1 @ q0 + 2j + 1} -- the layout wavelet_assemble_kernel
 //                unpacks with one PRMT per coefficient pair; it costs nothing here because the
 //                PRMT that files a symbol away takes any destination byte.
-#ifdef GST_STATIC_TAB
-constexpr bool kStaticTab = true;
-#else
-constexpr bool kStaticTab = false;
-#endif
-template <bool FULL, int NC, bool ILV, bool STAB, class Emit>
-__device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint32_t *tab_p, const uint8_t *__restrict__ stream,
+template <bool FULL, int NC, bool ILV, class Emit>
+__device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t *__restrict__ stream,
                                                    const uint32_t (&grp)[NC], uint32_t n_lanes, const uint32_t (&ring)[NC],
                                                    const uint8_t *buf_lo, const uint8_t *buf_hi, Emit emit) {
-  static_assert(!ILV || NC % 2 == 0, "interleaved output needs pairs of chains");
+  static_assert(!ILV || NC == 2, "interleaved output needs two chains");
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gt = lanemask_gt();
   const bool active = FULL || lane < n_lanes;
@@ -236,16 +236,9 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint32_
           // 8 KiB-aligned in the shared window) -- the mask-then-scale form costs two ALU-pipe instructions
           uint32_t s4;
           asm("mul.lo.u32 %0, %1, 4;" : "=r"(s4) : "r"(state[c]));
-          uint32_t e;
-          if (STAB) {
-            // the table is a static __shared__ array: its address is a link-time constant that rides in the
-            // immediate offset of the LDS, so the slot address is one AND and no register holds the table base
-            e = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(tab_p) + (s4 & (4 * kTableSize - 4)));
-          } else {
-            uint32_t slot_a;
-            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(slot_a) : "r"(s4), "n"(4 * kTableSize - 4), "r"(tab_s));
-            e = lds32(slot_a);
-          }
+          uint32_t slot_a;
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(slot_a) : "r"(s4), "n"(4 * kTableSize - 4), "r"(tab_s));
+          const uint32_t e = lds32(slot_a);
           // state' = (state >> 11) * freq + slot - cum (gst_kernels.cuh); the symbol shift is a multiply so that it
           // issues on the FMA pipe
           uint32_t sym24;
@@ -265,8 +258,8 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint32_
           if (ILV) {
             // byte 2 (q & 1) + c of word q / 2 <- symbol
             constexpr uint32_t kIns[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};
-            const int byte = 2 * (q & 1) + (c & 1);
-            uint32_t &a = acc[8 * (c >> 1) + (q >> 1)];  // chains 2j, 2j + 1 fill words 8j .. 8j + 7
+            const int byte = 2 * (q & 1) + c;
+            uint32_t &a = acc[q >> 1];
             a = byte == 0 ? __byte_perm(a, sym24, kIns[0]) : byte == 1 ? __byte_perm(a, sym24, kIns[1])
               : byte == 2 ? __byte_perm(a, sym24, kIns[2]) : __byte_perm(a, sym24, kIns[3]);
           } else {
@@ -287,18 +280,14 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint32_
 // spreads it -- the result is determined by the frequencies alone, so it is identical.
 // The kernel also zeroes `zero_words` 32-bit words at `zero` (the index-carry accumulators of the batch,
 // which rans_streams_kernel adds to): it is the first launch of a call, so no separate memset is needed.
-__global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__restrict__ freqs,
-                                                           uint32_t *__restrict__ tables, uint32_t *__restrict__ zero,
-                                                           uint32_t zero_words) {
-  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < zero_words; i += gridDim.x * 256) zero[i] = 0u;
-  __shared__ uint32_t s_freq[256];
-  __shared__ uint32_t s_cum[256];
-  __shared__ uint32_t s_sym[kTableSize];
-  __shared__ uint32_t s_warp[8];
+struct TableScratch {
+  uint32_t freq[256], cum[256], warp[8];
+};
+// 256 threads: frequencies f16[256] -> 2048 packed entries at `out` (global, or shared = `work`).  `work`: 2048 words
+// of shared memory.
+__device__ __forceinline__ void build_table_cta(const uint16_t *__restrict__ f16, uint32_t *work, uint32_t *out, TableScratch &ts) {
   const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const uint16_t *f16 = reinterpret_cast<const uint16_t *>(freqs + 512ull * blockIdx.x);
   const uint32_t f = f16[t];
-
   // exclusive scan of the 256 frequencies
   uint32_t inc = f;
 #pragma unroll
@@ -306,15 +295,15 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__rest
     const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += n;
   }
-  if (lane == 31) s_warp[warp] = inc;
-  for (int i = t; i < kTableSize; i += 256) s_sym[i] = 0;
+  if (lane == 31) ts.warp[warp] = inc;
+  for (int i = t; i < kTableSize; i += 256) work[i] = 0;
   __syncthreads();
   uint32_t base = 0;
-  for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+  for (uint32_t w = 0; w < warp; ++w) base += ts.warp[w];
   const uint32_t cum = (base + inc - f) & 0xFFFFu;  // ushort arithmetic, build_table.cl:14
-  s_freq[t] = f;
-  s_cum[t] = cum;
-  if (f != 0 && cum < kTableSize) s_sym[cum] = t;
+  ts.freq[t] = f;
+  ts.cum[t] = cum;
+  if (f != 0 && cum < kTableSize) work[cum] = t;
   __syncthreads();
 
   // inclusive max-scan over the 2048 slots, 8 consecutive slots per thread
@@ -322,7 +311,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__rest
   uint32_t run = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    run = max(run, s_sym[t * 8 + i]);
+    run = max(run, work[t * 8 + i]);
     v[i] = run;
   }
   uint32_t wmax = run;
@@ -332,19 +321,29 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__rest
     if (lane >= d) wmax = max(wmax, n);
   }
   __syncthreads();
-  if (lane == 31) s_warp[warp] = wmax;
+  if (lane == 31) ts.warp[warp] = wmax;
   __syncthreads();
   uint32_t prev = __shfl_up_sync(0xffffffffu, wmax, 1);
   if (lane == 0) prev = 0;
-  for (uint32_t w = 0; w < warp; ++w) prev = max(prev, s_warp[w]);
-
-  uint32_t *out = tables + static_cast<size_t>(kTableSize) * blockIdx.x;
+  for (uint32_t w = 0; w < warp; ++w) prev = max(prev, ts.warp[w]);
+  // (every thread has read its eight slots: `out` may be `work`)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const uint32_t slot = t * 8 + i;
     const uint32_t sym = max(v[i], prev);
-    out[slot] = pack_entry(sym, s_freq[sym], slot, s_cum[sym]);
+    out[slot] = pack_entry(sym, ts.freq[sym], slot, ts.cum[sym]);
   }
+}
+
+__global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__restrict__ freqs,
+                                                           uint32_t *__restrict__ tables, uint32_t *__restrict__ zero,
+                                                           uint32_t zero_words) {
+  pdl_launch_dependents();
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < zero_words; i += gridDim.x * 256) zero[i] = 0u;
+  __shared__ uint32_t s_sym[kTableSize];
+  __shared__ TableScratch ts;
+  build_table_cta(reinterpret_cast<const uint16_t *>(freqs + 512ull * blockIdx.x), s_sym,
+                  tables + static_cast<size_t>(kTableSize) * blockIdx.x, ts);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -360,7 +359,10 @@ struct ImageStreams {
 __device__ __forceinline__ ImageStreams image_streams(const BatchParams &p, uint32_t b) {
   ImageStreams s;
   const uint4 *tbl = reinterpret_cast<const uint4 *>(p.cmp);
-  const uint4 oo = __ldg(tbl + b), io = __ldg(tbl + p.n_images + b);
+  // (a single-image call may carry its eight offsets in the kernel parameters instead of the buffer: the frame
+  // streamer uploads a file as it lies and writes no offset table)
+  const uint4 oo = p.inline_off ? make_uint4(p.off8[0], p.off8[1], p.off8[2], p.off8[3]) : __ldg(tbl + b);
+  const uint4 io = p.inline_off ? make_uint4(p.off8[4], p.off8[5], p.off8[6], p.off8[7]) : __ldg(tbl + p.n_images + b);
   s.payload = p.cmp + p.off_region + 2048ull * p.n_images;
   s.out_off[0] = oo.x; s.out_off[1] = oo.y; s.out_off[2] = oo.z; s.out_off[3] = oo.w;
   s.in_off[0] = io.x;  s.in_off[1] = io.y;  s.in_off[2] = io.z;  s.in_off[3] = io.w;
@@ -423,21 +425,18 @@ struct RansSmem {
 };
 
 constexpr int kRansWarps = 8;
-// rANS groups per warp: NP plane-pair items = 2 NP chains.  NP = 2 (four chains in one instruction stream, 3 CTAs
-// = 96 chains per SM) for batches that fill the machine, NP = 1 (two chains, 5 CTAs = 80 chains per SM, twice the
-// CTAs) otherwise.
-template <int NP> struct RansCfg {
-  static constexpr int kChains = 2 * NP;
+// Two rANS groups (chains) per warp in one instruction stream, 5 CTAs = 40 warps = 80 chains per SM.  Measured
+// alternatives: four chains per warp at 3 CTAs (96 chains) 10 % slower, 4 CTAs of two chains 2.4 % slower -- the
+// kernel wants warps; one chain per warp for calls that leave SMs idle: no faster (a decode step of a lone warp
+// takes ~300 cycles with one chain or two), and the byte-granular stores of a lone plane cost more than they save.
+struct RansCfg {
+  static constexpr int kChains = 2;
   static constexpr int kGroupsPerCta = kRansWarps * kChains;
-#ifdef GST_STATIC_TAB
-  static constexpr int kSmem = kGroupsPerCta * kRingSlot;  // the table is a static array
-#else
   static constexpr int kSmem = kGroupsPerCta * kRingSlot + kTableSize * 4 + kRingSlot;  // + alignment slack
-#endif
 #ifdef GST_RANS_CTAS
   static constexpr int kCtasPerSm = GST_RANS_CTAS;
 #else
-  static constexpr int kCtasPerSm = NP == 1 ? 5 : 3;
+  static constexpr int kCtasPerSm = 5;
 #endif
 };
 
@@ -447,56 +446,51 @@ struct StreamGrid {
   __host__ __device__ uint32_t per_image() const { return y_ctas + c_ctas + pal_ctas + idx_ctas; }
 };
 
-// One warp's share of the Y or chroma stream: one group of plane A and the same group of plane B
-// of a plane pair -- pair 0 = (Y1, Y2), pair 1 = (Co1, Co2), pair 2 = (Cg1, Cg2), i.e. the two
-// endpoints' planes of one colour channel, which the wavelet and the assembly process as the two
-// 16-bit halves of one register.  Stream order (codec/encoder.cpp:87,93-95): Y = Y1 || Y2,
-// chroma = Co1 || Cg1 || Co2 || Cg2, every plane groups_per_plane groups long.
-template <bool TAP, int NP>
-__device__ __forceinline__ void rans_plane_pairs(const BatchParams &p, uint32_t b, uint32_t type, uint32_t item0,
-                                                 const uint8_t *stream, uint32_t out_off, uint32_t tab_s, const uint32_t *tab_p, const uint32_t (&ring)[2 * NP]) {
+// Group index inside the Y or chroma stream of plane `half` (0 = A, 1 = B) of plane pair `pair`, group g.
+// pair 0 = (Y1, Y2), pair 1 = (Co1, Co2), pair 2 = (Cg1, Cg2), i.e. the two endpoints' planes of one colour
+// channel, which the wavelet and the assembly process as the two 16-bit halves of one register.  Stream order
+// (codec/encoder.cpp:87,93-95): Y = Y1 || Y2, chroma = Co1 || Cg1 || Co2 || Cg2, every plane groups_per_plane long.
+__device__ __forceinline__ uint32_t plane_group(uint32_t pair, uint32_t half, uint32_t g, uint32_t gpp) {
+  if (half == 0) return pair == 2 ? gpp + g : g;
+  return pair == 0 ? gpp + g : pair == 1 ? 2 * gpp + g : 3 * gpp + g;
+}
+__device__ __forceinline__ uint8_t *pair_group_base(const BatchParams &p, uint32_t b, uint32_t pair, uint32_t g) {
+  return p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + (static_cast<size_t>(pair) * p.groups_per_plane + g) * (2 * kGroupSyms);
+}
+
+// One warp's share of the Y or chroma stream, two chains: the same group of the two planes of a pair.
+template <bool TAP>
+__device__ __forceinline__ void rans_plane_pair(const BatchParams &p, uint32_t b, uint32_t type, uint32_t item,
+                                                const uint8_t *stream, uint32_t out_off, uint32_t tab_s, const uint32_t (&ring)[2]) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gpp = p.groups_per_plane;
-  uint32_t grp[2 * NP];
-  uint8_t *dst[NP];
-#pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const uint32_t item = item0 + i;
-    const uint32_t pair = type == 0 ? 0u : 1u + item / gpp, g = item % gpp;
-    grp[2 * i] = pair == 2 ? gpp + g : g;
-    grp[2 * i + 1] = pair == 0 ? gpp + g : pair == 1 ? 2 * gpp + g : 3 * gpp + g;
-    dst[i] = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + (static_cast<size_t>(pair) * gpp + g) * (2 * kGroupSyms) + 15 * 1024 + lane * 32;
-  }
+  const uint32_t pair = type == 0 ? 0u : 1u + item / gpp, g = item % gpp;
+  const uint32_t grp[2] = {plane_group(pair, 0, g, gpp), plane_group(pair, 1, g, gpp)};
+  uint8_t *dst = pair_group_base(p, b, pair, g) + 15 * 1024 + lane * 32;
   uint8_t *tap = TAP && p.tap_symbols ? p.tap_symbols + out_off + lane * kSymsPerLane + 240 : nullptr;
-  rans_decode_groups<true, 2 * NP, true, kStaticTab>(tab_s, tab_p, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
-                                         [&](int m, const uint32_t (&w)[8 * NP]) {
+  rans_decode_groups<true, 2, true>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
+                                    [&](int m, const uint32_t (&w)[8]) {
+                                      *reinterpret_cast<uint4 *>(dst - 1024 * m) = make_uint4(w[0], w[1], w[2], w[3]);
+                                      *reinterpret_cast<uint4 *>(dst - 1024 * m + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                                      if (TAP && tap) {
 #pragma unroll
-                                           for (int i = 0; i < NP; ++i) {
-                                             *reinterpret_cast<uint4 *>(dst[i] - 1024 * m) = make_uint4(w[8 * i], w[8 * i + 1], w[8 * i + 2], w[8 * i + 3]);
-                                             *reinterpret_cast<uint4 *>(dst[i] - 1024 * m + 16) = make_uint4(w[8 * i + 4], w[8 * i + 5], w[8 * i + 6], w[8 * i + 7]);
-                                             if (TAP && tap) {
-#pragma unroll
-                                               for (int c = 0; c < 2; ++c) {
-                                                 const uint32_t sel = c ? 0x7531u : 0x6420u;
-                                                 *reinterpret_cast<uint4 *>(tap + static_cast<size_t>(grp[2 * i + c]) * kGroupSyms - 16 * m) =
-                                                     make_uint4(__byte_perm(w[8 * i], w[8 * i + 1], sel), __byte_perm(w[8 * i + 2], w[8 * i + 3], sel),
-                                                                __byte_perm(w[8 * i + 4], w[8 * i + 5], sel), __byte_perm(w[8 * i + 6], w[8 * i + 7], sel));
-                                               }
-                                             }
-                                           }
-                                         });
+                                        for (int c = 0; c < 2; ++c) {
+                                          const uint32_t sel = c ? 0x7531u : 0x6420u;
+                                          *reinterpret_cast<uint4 *>(tap + static_cast<size_t>(grp[c]) * kGroupSyms - 16 * m) =
+                                              make_uint4(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel),
+                                                         __byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel));
+                                        }
+                                      }
+                                    });
 }
 
 // One warp's share of the palette or index stream: NC consecutive groups starting at `group`.
-template <int NC, bool TAP, int NA>
+template <int NC, bool TAP>
 __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_t b, uint32_t type, uint32_t group,
                                                    const uint8_t *stream, uint32_t out_off, uint32_t pal_off,
-                                                   uint32_t tab_s, const uint32_t *tab_p, const uint32_t (&ring_all)[NA]) {
-  static_assert(NC <= NA, "not enough rings");
+                                                   uint32_t tab_s, const uint32_t (&ring)[NC]) {
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t grp[NC], ring[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) ring[c] = ring_all[c];
+  uint32_t grp[NC];
 
 #pragma unroll
   for (int c = 0; c < NC; ++c) grp[c] = group + c;
@@ -506,7 +500,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
     const uint64_t off = static_cast<uint64_t>(pal_off) + static_cast<uint64_t>(group) * kGroupSyms;
     const bool ok = off + NC * kGroupSyms <= p.palette_cap;
     uint8_t *dst = p.palette + off + lane * kSymsPerLane + 240;
-    rans_decode_groups<true, NC, false, kStaticTab>(tab_s, tab_p, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
+    rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                         [&](int m, const uint32_t (&w)[NC * 4]) {
 #pragma unroll
                                           for (int c = 0; c < NC; ++c) {
@@ -525,7 +519,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   uint16_t *dst16 = reinterpret_cast<uint16_t *>(p.idx_s) + t0;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(p.idx_s) + t0;
   const bool idx16 = p.idx16 != 0;
-  rans_decode_groups<true, NC, false, kStaticTab>(tab_s, tab_p, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
+  rans_decode_groups<true, NC, false>(tab_s, stream, grp, kLanes, ring, p.cmp, p.cmp + p.cmp_bytes,
                                [&](int m, const uint32_t (&wa)[NC * 4]) {
 #pragma unroll
                                  for (int c = 0; c < NC; ++c) {
@@ -570,25 +564,21 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   }
 }
 
-template <bool TAP, int NP>
-__global__ void __launch_bounds__(kRansWarps * 32, RansCfg<NP>::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
-  constexpr int NC = RansCfg<NP>::kChains;
+// FT (fused tables): the CTA builds its decode table in shared memory from the 512-byte frequency block of its
+// stream (stage 1, ans/build_table.cl) instead of loading the 8 KiB build_tables_kernel left in global memory.  For
+// calls too small to fill the machine this removes a launch and its dependency from the critical path; for large
+// batches every table would be built by up to eight CTAs instead of once, so they keep the separate kernel.
+template <bool TAP, bool FT>
+__global__ void __launch_bounds__(kRansWarps * 32, RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+  constexpr int NC = RansCfg::kChains;
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
+  const RansSmem lay(smem_u32(smem));
   const uint32_t warp = threadIdx.x >> 5;
   uint32_t ring[NC];
-#ifdef GST_STATIC_TAB
-  __shared__ __align__(16) uint32_t s_tab[kTableSize];
-  const uint32_t *tab_p = s_tab;
-  const uint32_t tab_s = smem_u32(s_tab);
-#pragma unroll
-  for (int c = 0; c < NC; ++c) ring[c] = smem_u32(smem) + (NC * warp + c) * kRingSlot + kChunk;
-#else
-  const RansSmem lay(smem_u32(smem));
 #pragma unroll
   for (int c = 0; c < NC; ++c) ring[c] = lay.ring(NC * warp + c);
   const uint32_t tab_s = lay.tab;
-  const uint32_t *tab_p = nullptr;
-#endif
 
   const uint32_t per_image = sg.per_image();
   const uint32_t b = blockIdx.x / per_image;
@@ -603,37 +593,32 @@ __global__ void __launch_bounds__(kRansWarps * 32, RansCfg<NP>::kCtasPerSm) rans
   const uint32_t in_off = type == 0 ? is.in_off[0] : type == 1 ? is.in_off[1] : type == 2 ? is.in_off[2] : is.in_off[3];
   const uint32_t out_off = type == 0 ? is.out_off[0] : type == 1 ? is.out_off[1] : type == 2 ? is.out_off[2] : is.out_off[3];
   const uint8_t *stream = is.payload + in_off;
-  if (type < 2) {
-    // work items of a plane stream: (pair, group); Y has groups_per_plane of them, chroma twice as many
-    const uint32_t n_items = (type + 1) * p.groups_per_plane;
-    if (r * kRansWarps * NP >= n_items) return;
+  // chains of this CTA's stream: plane streams count one per (plane, group)
+  const uint32_t n_chains = type == 0 ? 2 * p.groups_per_plane : type == 1 ? 4 * p.groups_per_plane
+                          : type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
+  const uint32_t first = r * RansCfg::kGroupsPerCta;
+  if (first >= n_chains) return;
+  if (FT) {
+    __shared__ TableScratch ts;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + (lay.tab - lay.s0));
+    build_table_cta(reinterpret_cast<const uint16_t *>(p.cmp + p.off_region + 2048ull * b + 512u * type), tab, tab, ts);
+  } else {
+    pdl_wait();  // (the tables and the zeroed index carries come from build_tables_kernel)
     load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
-    __syncthreads();
-    const uint32_t item = (r * kRansWarps + warp) * NP;
-    if (item >= n_items) return;
-    if (NP == 1 || item + 1 < n_items) {
-      rans_plane_pairs<TAP, NP>(p, b, type, item, stream, out_off, tab_s, tab_p, ring);
-    } else {
-      const uint32_t ring1[2] = {ring[0], ring[1]};
-      rans_plane_pairs<TAP, 1>(p, b, type, item, stream, out_off, tab_s, tab_p, ring1);
-    }
+  }
+  __syncthreads();
+  const uint32_t chain = first + warp * NC;
+  if (chain >= n_chains) return;
+  if (type < 2) {
+    // (plane streams always hold an even number of chains: the two planes of every pair)
+    rans_plane_pair<TAP>(p, b, type, chain >> 1, stream, out_off, tab_s, ring);
     return;
   }
-  const uint32_t n_groups = type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
-  const uint32_t first = r * RansCfg<NP>::kGroupsPerCta;
-  if (first >= n_groups) return;
-  load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
-  __syncthreads();
-  const uint32_t group = first + warp * NC;
-  if (group >= n_groups) return;
-  const uint32_t left = n_groups - group;
-  if (NC == 4 && left >= 4) {
-    rans_stream_groups<NC, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, tab_p, ring);
+  if (chain + 1 < n_chains) {
+    rans_stream_groups<2, TAP>(p, b, type, chain, stream, out_off, is.pal_off, tab_s, ring);
   } else {
-    // tail: two chains at a time, then one
-    if (left >= 2) rans_stream_groups<2, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, tab_p, ring);
-    if (NC == 4 && left == 3) rans_stream_groups<1, TAP>(p, b, type, group + 2, stream, out_off, is.pal_off, tab_s, tab_p, ring);
-    if (left == 1) rans_stream_groups<1, TAP>(p, b, type, group, stream, out_off, is.pal_off, tab_s, tab_p, ring);
+    const uint32_t ring1[1] = {ring[0]};
+    rans_stream_groups<1, TAP>(p, b, type, chain, stream, out_off, is.pal_off, tab_s, ring1);
   }
 }
 
@@ -930,6 +915,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   if (tile >= p.n_blocks / kTileSyms) return;
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
+  pdl_wait();  // everything below reads what rans_streams_kernel wrote
 
   // ---- the tile's coefficients: sym_t -> raw halves of the W rows -------------------------------
   {
@@ -950,7 +936,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
 
   // out_off[4b..4b+3] of this image (codec/decoder.cpp:430-463): requested now, first used after the
   // lower wavelet levels, so the warp never waits for it
-  const uint4 out_off = __ldg(reinterpret_cast<const uint4 *>(p.cmp) + b);
+  const uint4 out_off = p.inline_off ? make_uint4(p.off8[0], p.off8[1], p.off8[2], p.off8[3]) : __ldg(reinterpret_cast<const uint4 *>(p.cmp) + b);
   uint32_t n_entries = 0;
   bool pal_ok = false;
   const uint32_t *pal = nullptr;
@@ -1191,7 +1177,7 @@ __global__ void __launch_bounds__(kPlainWarps * 32)
   const bool active = lane < n_lanes;
   const uint32_t grp[1] = {group};
   const uint32_t ring[1] = {lay.ring(warp)};
-  rans_decode_groups<false, 1, false, false>(tab_s, nullptr, data, grp, n_lanes, ring, data, data + data_bytes,
+  rans_decode_groups<false, 1, false>(tab_s, data, grp, n_lanes, ring, data, data + data_bytes,
                                       [&](int m, const uint32_t (&w)[4]) {
                                         if (active) *reinterpret_cast<uint4 *>(dst - 16 * m) = make_uint4(w[0], w[1], w[2], w[3]);
                                       });
@@ -1304,17 +1290,34 @@ static cudaError_t ensure_attrs() {
                     wavelet_assemble_kernel<0, true, false>, wavelet_assemble_kernel<1, true, false>}) {
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem)) != cudaSuccess) return e;
     }
-    for (auto *k : {rans_streams_kernel<false, 1>, rans_streams_kernel<true, 1>}) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RansCfg<1>::kSmem)) != cudaSuccess) return e;
+    for (auto *k : {rans_streams_kernel<false, false>, rans_streams_kernel<true, false>, rans_streams_kernel<false, true>,
+                    rans_streams_kernel<true, true>}) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RansCfg::kSmem)) != cudaSuccess) return e;
     }
-#if defined(GST_RANS_NP) && GST_RANS_NP == 2
-    for (auto *k : {rans_streams_kernel<false, 2>, rans_streams_kernel<true, 2>}) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RansCfg<2>::kSmem)) != cudaSuccess) return e;
-    }
-#endif
     return cudaFuncSetAttribute(ans_decode_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem);
   }();
   return once;
+}
+
+// A launch that may start while the previous kernel of the stream is still draining (programmatic dependent
+// launch): the kernel runs its prologue and blocks in griddepcontrol.wait until that kernel has completed.
+template <class... KArgs, class... Args>
+static cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+bool is_small_call(uint32_t n_images, uint32_t groups_per_plane, uint32_t max_palette_bytes) {
+  return static_cast<uint64_t>(n_images) * (7ull * groups_per_plane + max_palette_bytes / kGroupSyms) <= kSmallCallGroups;
 }
 
 cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,
@@ -1324,50 +1327,55 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   if (e != cudaSuccess) return e;
   int mark = 0;
   auto stamp = [&]() { return marks ? cudaEventRecord(marks[mark++], s) : cudaSuccess; };
+  const bool pdl = marks == nullptr;  // (an event between two kernels serialises them anyway)
   if ((e = stamp()) != cudaSuccess) return e;
-  // stage 1: 4 tables per image, straight from the freq region of the compressed buffer
-  e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s, reinterpret_cast<uint32_t *>(p.idx_carry),
-                          p.n_images * p.groups_per_plane);
+  // A call whose rANS groups do not fill the machine is bound by the latency of one group (256 dependent decode
+  // steps) plus whatever precedes it: the consuming CTAs build their tables themselves, two launches.  Everything
+  // else: tables built once per stream by their own kernel, three launches.
+  const bool small = is_small_call(p.n_images, p.groups_per_plane, max_palette_bytes);
+  const uint32_t carry_words = p.n_images * p.groups_per_plane;
+  if (small) {
+    e = cudaMemsetAsync(p.idx_carry, 0, 4ull * carry_words, s);
+  } else {
+    // stage 1: 4 tables per image, straight from the freq region of the compressed buffer
+    e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s, reinterpret_cast<uint32_t *>(p.idx_carry), carry_words);
+  }
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
-  // Two chains per warp (NP = 1).  Four chains per warp at 3 CTAs per SM (96 chains instead of 80, -DGST_RANS_NP=2)
-  // was measured 10 % slower: the kernel wants warps, not chains per warp.
-#ifdef GST_RANS_NP
-  constexpr int np = GST_RANS_NP;
-#else
-  constexpr int np = 1;
-#endif
-  const uint32_t items_per_cta = kRansWarps * np, groups_per_cta = kRansWarps * 2 * np;
+  const uint32_t per_cta = RansCfg::kGroupsPerCta;
   StreamGrid sg;
-  sg.y_ctas = (p.groups_per_plane + items_per_cta - 1) / items_per_cta;      // NP (plane pair, group) items per warp
-  sg.c_ctas = (2 * p.groups_per_plane + items_per_cta - 1) / items_per_cta;
-  sg.pal_ctas = (max_palette_bytes / kGroupSyms + groups_per_cta - 1) / groups_per_cta;
-  sg.idx_ctas = (p.groups_per_plane + groups_per_cta - 1) / groups_per_cta;
+  sg.y_ctas = (2 * p.groups_per_plane + per_cta - 1) / per_cta;
+  sg.c_ctas = (4 * p.groups_per_plane + per_cta - 1) / per_cta;
+  sg.pal_ctas = (max_palette_bytes / kGroupSyms + per_cta - 1) / per_cta;
+  sg.idx_ctas = (p.groups_per_plane + per_cta - 1) / per_cta;
   // the stage taps (parity tests only) are a separate instantiation: the production kernels carry none of that code
   const bool taps = p.tap_symbols || p.tap_planes || p.tap_indices;
-  const uint32_t rans_grid = p.n_images * sg.per_image();
-  if (taps) rans_streams_kernel<true, np><<<rans_grid, kRansWarps * 32, RansCfg<np>::kSmem, s>>>(p, sg);
-  else rans_streams_kernel<false, np><<<rans_grid, kRansWarps * 32, RansCfg<np>::kSmem, s>>>(p, sg);
-  e = cudaGetLastError();
+  const dim3 rans_grid(p.n_images * sg.per_image()), rans_block(kRansWarps * 32);
+  if (small) {
+    e = taps ? launch_kernel(rans_streams_kernel<true, true>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg)
+             : launch_kernel(rans_streams_kernel<false, true>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg);
+  } else {
+    e = taps ? launch_kernel(rans_streams_kernel<true, false>, rans_grid, rans_block, RansCfg::kSmem, s, pdl, p, sg)
+             : launch_kernel(rans_streams_kernel<false, false>, rans_grid, rans_block, RansCfg::kSmem, s, pdl, p, sg);
+  }
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
   // stages 4 + 5 (and the cross-group carry of stage 3): one warp per tile
   if (p.n_images > 65535u) return cudaErrorInvalidValue;  // grid.y; gst_capi.cu pages larger batches
-  const dim3 grid((p.n_blocks / kTileSyms + kWaWarps - 1) / kWaWarps, p.n_images);
-  auto launch = [&](auto kern) { kern<<<grid, kWaWarps * 32, kWaSmem, s>>>(p); };
+  const dim3 grid((p.n_blocks / kTileSyms + kWaWarps - 1) / kWaWarps, p.n_images), block(kWaWarps * 32);
+  auto launch = [&](auto kern) { return launch_kernel(kern, grid, block, kWaSmem, s, pdl, p); };
   const int variant = (rgb_mode ? 1 : 0) | (taps ? 2 : 0) | (p.idx16 ? 4 : 0);
   switch (variant) {
-    case 0: launch(wavelet_assemble_kernel<0, false, false>); break;
-    case 1: launch(wavelet_assemble_kernel<1, false, false>); break;
-    case 2: launch(wavelet_assemble_kernel<0, true, false>); break;
-    case 3: launch(wavelet_assemble_kernel<1, true, false>); break;
-    case 4: launch(wavelet_assemble_kernel<0, false, true>); break;
-    case 5: launch(wavelet_assemble_kernel<1, false, true>); break;
-    case 6: launch(wavelet_assemble_kernel<0, true, true>); break;
-    default: launch(wavelet_assemble_kernel<1, true, true>); break;
+    case 0: e = launch(wavelet_assemble_kernel<0, false, false>); break;
+    case 1: e = launch(wavelet_assemble_kernel<1, false, false>); break;
+    case 2: e = launch(wavelet_assemble_kernel<0, true, false>); break;
+    case 3: e = launch(wavelet_assemble_kernel<1, true, false>); break;
+    case 4: e = launch(wavelet_assemble_kernel<0, false, true>); break;
+    case 5: e = launch(wavelet_assemble_kernel<1, false, true>); break;
+    case 6: e = launch(wavelet_assemble_kernel<0, true, true>); break;
+    default: e = launch(wavelet_assemble_kernel<1, true, true>); break;
   }
-  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return stamp();
 }

@@ -64,6 +64,8 @@ struct BatchParams {
   int32_t *idx_carry;        // [B][N/8192] sum of the index groups BEFORE each group (accumulated with atomics)
   // outputs
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
+  uint32_t inline_off;       // 1: n_images == 1 and the offset table is off8 below, not the first 32 bytes of cmp
+  uint32_t off8[8];          // out_off[0..3], in_off[0..3] of that image
   uint32_t kc[8];            // packed constants the wavelet kernel wants in the constant bank (fill_kernel_constants)
   // optional taps for the stage parity tests (NULL in production)
   uint8_t *tap_symbols;      // reference decmp_buf layout: image b stream s at out_off[4b+s]
@@ -94,7 +96,10 @@ cudaError_t launch_ans_encode(const uint8_t *symbols, uint32_t n_groups, const u
                               uint32_t *sizes, cudaStream_t s);
 cudaError_t launch_ans_encode_gather(const uint8_t *scratch, const uint32_t *sizes, const uint32_t *offsets,
                                      uint32_t n_groups, uint8_t *out, cudaStream_t s);
-// number of kernels launch_decode_batch enqueues (for bench.py's gpu_launches)
+// kernels launch_decode_batch enqueues: 3 (tables, rANS, wavelet + assembly), or 2 for a "small" call -- one whose
+// rANS groups do not fill the machine (is_small_call): tables built by the consuming CTAs
 constexpr int kLaunchesPerBatch = 3;
+constexpr uint32_t kSmallCallGroups = 4096;
+bool is_small_call(uint32_t n_images, uint32_t groups_per_plane, uint32_t max_palette_bytes);
 
 }  // namespace gst

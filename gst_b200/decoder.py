@@ -405,11 +405,17 @@ class FrameStreamer:
         check(lib().gst_streamer_create(dec.ctx, width, height, depth, int(mode), C.byref(h)))
         self.handle = h
 
-    def submit(self, frame, out=None):
-        """frame: .gst bytes (numpy array or PinnedBuffer); out: optional DeviceBuffer.  Returns the ticket."""
+    def submit(self, frame, out=None, host_out=None, direct=False):
+        """frame: .gst bytes (numpy array or PinnedBuffer); out: optional DeviceBuffer; host_out: optional host
+        address the decoded frame is also copied to (on the slot's stream, covered by wait()); direct: upload
+        straight from `frame`, which must then stay valid until wait().  Returns the ticket."""
         ptr, n = (frame.ptr, frame.nbytes) if isinstance(frame, PinnedBuffer) else (_as_u8(frame).ctypes.data, _as_u8(frame).size)
         t = C.c_uint64()
-        check(lib().gst_streamer_submit(self.handle, ptr, n, out.ptr if out is not None else None, C.byref(t)))
+        if host_out is None and not direct:
+            check(lib().gst_streamer_submit(self.handle, ptr, n, out.ptr if out is not None else None, C.byref(t)))
+        else:
+            check(lib().gst_streamer_submit_ex(self.handle, ptr, n, out.ptr if out is not None else None, host_out,
+                                               1 if direct else 0, C.byref(t)))
         return t.value
 
     def wait(self, ticket):

@@ -104,7 +104,8 @@ int gst_pack_batch(const uint8_t *const *gst_files, const size_t *lens, uint32_t
  * (4*2048*6 + 17N + P), which upper-bounds what this implementation uses (32 KB + 4N + P +
  * 8N/8192), so callers that size by it keep working.  With a preallocated arena regions are
  * bump-allocated and never reset until gst_free_scratch (codec/decoder.cpp:74-82); without
- * one each call uses a stream-ordered allocation released when the call's work completes. */
+ * one the calls made on a stream share one grow-only buffer the context keeps for that stream
+ * (released by gst_free_scratch / gst_ctx_destroy): a call in steady state allocates nothing. */
 size_t gst_required_scratch(const gst_header *hdr);
 int gst_preallocate(gst_ctx *ctx, size_t bytes);
 int gst_free_scratch(gst_ctx *ctx);
@@ -145,8 +146,8 @@ int gst_load_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const siz
 
 /* ---- frame streamer: the headless form of the demo player (demo/demo.cpp:145-243,504-600), which
  * reads frameNNNN.gtc, uploads it, calls LoadCompressedDXT / LoadRGB and blocks on the event
- * before the next frame.  Here `depth` frames are in flight: submit() packs the frame into the
- * slot's pinned staging, copies it to the device and decodes it on the slot's own stream; it only
+ * before the next frame.  Here `depth` frames are in flight: submit() copies the frame into the
+ * slot's pinned staging, uploads it and decodes it on the slot's own stream; it only
  * blocks when the slot's previous frame (ticket - depth) is still running.  mode 0 = DXT1, 1 = RGB8
  * (LoadRGB, demo/demo.cpp:208-212).  out_dev NULL decodes into the slot's own device frame.
  * wait() blocks until that frame is complete and returns where it was decoded to; a frame stays
@@ -156,6 +157,14 @@ int gst_streamer_create(gst_ctx *ctx, uint32_t width, uint32_t height, uint32_t 
                         gst_streamer **out);
 int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev,
                         uint64_t *ticket);
+/* submit with options.  out_host (may be NULL): the decoded frame is also copied to this host buffer (pinned for full
+ * speed) on the slot's own stream, and wait() returns when the copy has landed -- the demo's
+ * "decode, then hand the frame on" (demo/demo.cpp:221-237) without a separate download the caller has to order
+ * against the slot's next frame.  GST_SUBMIT_DIRECT: no copy into the slot's staging -- the upload reads the
+ * caller's .gst buffer, which must stay valid (and should be pinned) until the frame has been waited for. */
+#define GST_SUBMIT_DIRECT 1u
+int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, void *out_host,
+                           uint32_t flags, uint64_t *ticket);
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev);
 void gst_streamer_destroy(gst_streamer *st);
 
@@ -208,13 +217,16 @@ int gst_ans_encode_stream(gst_ctx *ctx, const uint8_t *symbols, size_t n_symbols
 
 /* stage 1 on caller buffers: n tables of 256 x u16 frequencies (512 B each, as stored in
  * the .gst file) -> n x 2048 packed u32 entries
- * freq | sym << 11 | bias' << 19 (gst_kernels.cuh). */
+ * freq | sym << 12 | (slot - cum_freq) << 20 (gst_kernels.cuh). */
 int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t n_tables,
                      void *tables_dev);
 
 /* number of kernel launches one gst_load_*_batch call enqueues, in launch order:
- * build_tables, rans_streams (all four streams + the group-local index scan), wavelet_assemble */
+ * build_tables, rans_streams (all four streams + the group-local index scan), wavelet_assemble.
+ * gst_launches_for_batch: the number for these headers -- 2 when the call is too small to fill the GPU (at most
+ * 4096 rANS groups): the consuming CTAs build their tables themselves. */
 int gst_launches_per_batch(void);
+int gst_launches_for_batch(const gst_header *hdrs, uint32_t n);
 
 /* Per-kernel device timing for the benchmark's roofline line (no reference equivalent; the
  * reference only has wall-clock prints, demo/photos_sf.cpp:851,892-893).  While enabled,
