@@ -382,13 +382,7 @@ def main():
             # configs[4]: the demo player loop (demo/demo.cpp:145-243) with `depth` frames in flight: every frame is
             # uploaded from where it lies, decoded and copied back to the host on its slot's stream; a frame is
             # waited for `depth - 1` submissions after its own
-            tickets = []
-            for f in range(images):
-                tickets.append(streamer.submit(pin_files[order[f]], host_out=pin_out.ptr + f * 8 * N, direct=True))
-                if f >= args.depth - 1:
-                    streamer.wait(tickets[f - (args.depth - 1)])
-            for k in range(max(0, images - (args.depth - 1)), images):
-                streamer.wait(tickets[k])
+            streamer.play(ptrs, lens, images, host_out=pin_out.ptr, direct=True)
 
         pin_out.array[:] = 0xEE
         e2e_step()  # warm-up: grows the staging buffers
@@ -405,7 +399,7 @@ def main():
                "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(d2h_job),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
-               "api": "gst_streamer_submit_ex (direct upload, read-back on the slot's stream) + gst_streamer_wait per frame"
+               "api": "gst_streamer_play (per frame: direct upload, decode, read-back on the slot's stream)"
                       if streamer is not None else "gst_decompress_host_batch",
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
         if streamer is not None:

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "gst_streamer_create": (_int, [_vp, _u32, _u32, _u32, _int, C.POINTER(_vp)]),
     "gst_streamer_submit": (_int, [_vp, _vp, _sz, _vp, C.POINTER(C.c_uint64)]),
     "gst_streamer_submit_ex": (_int, [_vp, _vp, _sz, _vp, _vp, _u32, C.POINTER(C.c_uint64)]),
+    "gst_streamer_play": (_int, [_vp, _pp, C.POINTER(_sz), _u32, _vp, _vp, _u32]),
     "gst_streamer_wait": (_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "gst_streamer_destroy": (None, [_vp]),
     "gst_load_dxt_batch_tapped": (_int, [_vp, _hdr_p, _u32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),

@@ -292,7 +292,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.palette_cap = L.palette_total;
   p.idx_s = scratch + L.idx_off;
   p.idx16 = L.idx16 ? 1u : 0u;
-  p.idx_carry = reinterpret_cast<int32_t *>(scratch + L.total_off);
+  p.idx_total = reinterpret_cast<int32_t *>(scratch + L.total_off);
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
   gst::fill_kernel_constants(&p);
@@ -989,6 +989,27 @@ int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, voi
                            uint32_t flags, uint64_t *ticket) {
   if (flags & ~static_cast<uint32_t>(GST_SUBMIT_DIRECT)) return fail(GST_ERR_INVALID, "unknown submit flags 0x%x", flags);
   return streamer_submit(st, gst, len, out_dev, out_host, ticket, (flags & GST_SUBMIT_DIRECT) != 0);
+}
+
+// The demo's main loop (demo/demo.cpp:504-600: for every frame load the file, decode it, hand it on) over a sequence
+// that is already in host memory, `depth` frames in flight.
+int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size_t *lens, uint32_t n, void *out_dev,
+                      void *out_host, uint32_t flags) {
+  if (!st || !frames || !lens) return fail(GST_ERR_INVALID, "null argument");
+  const uint64_t first = st->next_ticket;
+  const uint32_t lag = st->depth - 1;
+  for (uint32_t f = 0; f < n; ++f) {
+    uint8_t *od = out_dev ? static_cast<uint8_t *>(out_dev) + static_cast<size_t>(f) * st->frame_bytes : nullptr;
+    uint8_t *oh = out_host ? static_cast<uint8_t *>(out_host) + static_cast<size_t>(f) * st->frame_bytes : nullptr;
+    int rc = gst_streamer_submit_ex(st, frames[f], lens[f], od, oh, flags, nullptr);
+    if (rc) return rc;
+    if (f >= lag && (rc = gst_streamer_wait(st, first + f - lag, nullptr))) return rc;
+  }
+  for (uint32_t f = n > lag ? n - lag : 0; f < n; ++f) {
+    int rc = gst_streamer_wait(st, first + f, nullptr);
+    if (rc) return rc;
+  }
+  return GST_OK;
 }
 
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev) {

@@ -278,8 +278,6 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
 // symbol x with cum[x] <= slot < cum[x+1].  The reference scans then binary-searches per slot;
 // here every symbol with a non-zero frequency drops its id at slot cum[x] and a max-scan
 // spreads it -- the result is determined by the frequencies alone, so it is identical.
-// The kernel also zeroes `zero_words` 32-bit words at `zero` (the index-carry accumulators of the batch,
-// which rans_streams_kernel adds to): it is the first launch of a call, so no separate memset is needed.
 struct TableScratch {
   uint32_t freq[256], cum[256], warp[8];
 };
@@ -335,11 +333,8 @@ __device__ __forceinline__ void build_table_cta(const uint16_t *__restrict__ f16
   }
 }
 
-__global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__restrict__ freqs,
-                                                           uint32_t *__restrict__ tables, uint32_t *__restrict__ zero,
-                                                           uint32_t zero_words) {
+__global__ void __launch_bounds__(256) build_tables_kernel(const uint8_t *__restrict__ freqs, uint32_t *__restrict__ tables) {
   pdl_launch_dependents();
-  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < zero_words; i += gridDim.x * 256) zero[i] = 0u;
   __shared__ uint32_t s_sym[kTableSize];
   __shared__ TableScratch ts;
   build_table_cta(reinterpret_cast<const uint16_t *>(freqs + 512ull * blockIdx.x), s_sym,
@@ -546,9 +541,8 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
                                    }
                                  }
                                });
-  // group-local inclusive prefix at the end of every run; the group total goes into the carry of every later
-  // group of the image (the cross-group part of stage 3, codec/decode_indices.cl:66-84: integer atomics,
-  // so the order of arrival does not matter; build_tables_kernel zeroed the accumulators)
+  // group-local inclusive prefix at the end of every run, and the group's total: wavelet_assemble_kernel adds the
+  // totals of the earlier groups of the image (the cross-group part of stage 3, codec/decode_indices.cl:66-84)
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     uint32_t inc = sum[c];
@@ -558,9 +552,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
       if (lane >= d) inc += n;
     }
     p.run_end[static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + (group + c) * kLanes + lane] = static_cast<int32_t>(inc);
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    int32_t *carry = p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane;
-    for (uint32_t g = group + c + 1 + lane; g < p.groups_per_plane; g += 32) atomicAdd(carry + g, static_cast<int32_t>(total));
+    if (lane == 31) p.idx_total[static_cast<size_t>(b) * p.groups_per_plane + group + c] = static_cast<int32_t>(inc);
   }
 }
 
@@ -603,7 +595,7 @@ __global__ void __launch_bounds__(kRansWarps * 32, RansCfg::kCtasPerSm) rans_str
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + (lay.tab - lay.s0));
     build_table_cta(reinterpret_cast<const uint16_t *>(p.cmp + p.off_region + 2048ull * b + 512u * type), tab, tab, ts);
   } else {
-    pdl_wait();  // (the tables and the zeroed index carries come from build_tables_kernel)
+    pdl_wait();  // (the tables come from build_tables_kernel)
     load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
   }
   __syncthreads();
@@ -943,15 +935,34 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
 
   // ---- assembly inputs of slab 0 start their trip now ---------------------------------
   const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
-  // index prefix at the end of a run = its group-local prefix + the carry of the earlier groups (both from
-  // rans_streams_kernel).  The 32 blocks of a tile row lie in one 256-block run, so lane l fetches the run end
-  // of tile row l once, now, and the slabs pick theirs up with a shuffle.
-  uint32_t re_row;
-  {
-    const uint32_t g_row = (ty * kTile + lane) * p.blocks_x + tx * kTile;
-    re_row = static_cast<uint32_t>(__ldg(p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + g_row / kSymsPerLane)) +
-             static_cast<uint32_t>(__ldg(p.idx_carry + static_cast<size_t>(b) * p.groups_per_plane + g_row / kGroupSyms));
-  }
+  // index prefix at the end of a run = its group-local prefix (rans_streams_kernel) + the totals of the earlier
+  // index groups of the image.  The 32 blocks of a tile row lie in one 256-block run, so lane l fetches the run end
+  // of tile row l once and the slabs pick theirs up with a shuffle.  The carry: the warp sums the totals of
+  // the groups before the tile's first one (lanes stride over them, one REDUX), then walks the few groups the 32
+  // rows span -- no atomics, no accumulator to zero between calls.
+  // The loads start now; the sum is taken once the tile's coefficients have arrived (resolve_run_ends below), so
+  // that no warp waits for them alone.
+  const uint32_t g_row = (ty * kTile + lane) * p.blocks_x + tx * kTile;
+  const uint32_t grp = g_row / kGroupSyms;
+  const uint32_t g_first = (ty * kTile * p.blocks_x + tx * kTile) / kGroupSyms;                 // group of tile row 0
+  const uint32_t g_last = ((ty * kTile + kTile - 1) * p.blocks_x + tx * kTile) / kGroupSyms;    // ... of tile row 31
+  const int32_t *tot = p.idx_total + static_cast<size_t>(b) * p.groups_per_plane;
+  const int32_t tot_lane = lane < g_first ? __ldg(tot + lane) : 0;   // this lane's share of the groups before the tile
+  const int32_t tot_first = __ldg(tot + g_first);
+  uint32_t re_row = static_cast<uint32_t>(__ldg(p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + g_row / kSymsPerLane));
+  auto resolve_run_ends = [&]() {
+    int32_t part = tot_lane;
+#pragma unroll 1  // (code size: the kernel has to stay inside the 32 KiB L1.5 instruction cache)
+    for (uint32_t g = lane + 32; g < g_first; g += 32) part += __ldg(tot + g);   // (images beyond 2048 x 2048 only)
+    int32_t carry = __reduce_add_sync(0xffffffffu, part);
+    if (grp > g_first) carry += tot_first;
+#pragma unroll 1
+    for (uint32_t g = g_first + 1; g < g_last; ++g) {                            // (tile rows spanning > 2 groups only)
+      const int32_t t = __ldg(tot + g);
+      if (grp > g) carry += t;
+    }
+    re_row += static_cast<uint32_t>(carry);
+  };
   // first block of this lane in slab k (rows 4k..4k+3 of the tile)
   const uint32_t gidx0 = (ty * kTile + (lane >> 3)) * p.blocks_x + tx * kTile + 4 * (lane & 7);
   const uint32_t slab_stride = 4 * p.blocks_x;
@@ -1005,6 +1016,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   asm volatile("" : "+r"(k10));  // keep it in a register (PRMT takes no immediate source)
   cp_async_wait_group<0>();
   __syncwarp();
+  resolve_run_ends();  // (its loads were issued with the tile's: they have landed too)
   // r3 / r1 come from the kernel parameters: as literals ptxas rematerialises them with a MOV before every use
   const ShiftK sk{p.kc[0], p.kc[1], p.kc[3], p.kc[4], p.kc[5], p.kc[6]};
   low_level_p<2>(w_s, lane, k10, sk);
@@ -1275,10 +1287,9 @@ __global__ void __launch_bounds__(256) ans_encode_gather_kernel(const uint8_t *_
 
 // ---------------------------------------------------------------------------------------
 // launchers
-cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,
-                                cudaStream_t s, uint32_t *zero, uint32_t zero_words) {
+cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables, cudaStream_t s) {
   if (n_tables == 0) return cudaSuccess;
-  build_tables_kernel<<<n_tables, 256, 0, s>>>(freqs, tables, zero, zero_words);
+  build_tables_kernel<<<n_tables, 256, 0, s>>>(freqs, tables);
   return cudaGetLastError();
 }
 
@@ -1333,14 +1344,11 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   // steps) plus whatever precedes it: the consuming CTAs build their tables themselves, two launches.  Everything
   // else: tables built once per stream by their own kernel, three launches.
   const bool small = is_small_call(p.n_images, p.groups_per_plane, max_palette_bytes);
-  const uint32_t carry_words = p.n_images * p.groups_per_plane;
-  if (small) {
-    e = cudaMemsetAsync(p.idx_carry, 0, 4ull * carry_words, s);
-  } else {
+  if (!small) {
     // stage 1: 4 tables per image, straight from the freq region of the compressed buffer
-    e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s, reinterpret_cast<uint32_t *>(p.idx_carry), carry_words);
+    e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s);
+    if (e != cudaSuccess) return e;
   }
-  if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch
   const uint32_t per_cta = RansCfg::kGroupsPerCta;

@@ -61,7 +61,7 @@ struct BatchParams {
   void *idx_s;               // [B][N] u16 or u32, transposed like sym_t: sum of the index deltas after block i in its 256-block run
   uint32_t idx16;            // 1: idx_s holds u16 (every palette <= 65536 entries), 0: u32
   int32_t *run_end;          // [B][N/256] group-local inclusive index prefix at the end of every run
-  int32_t *idx_carry;        // [B][N/8192] sum of the index groups BEFORE each group (accumulated with atomics)
+  int32_t *idx_total;        // [B][N/8192] sum of the index deltas of each index group
   // outputs
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
   uint32_t inline_off;       // 1: n_images == 1 and the offset table is off8 below, not the first 32 bytes of cmp
@@ -80,8 +80,7 @@ inline void fill_kernel_constants(BatchParams *p) {
 }
 
 // launch helpers (gst_kernels.cu)
-cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables,
-                                cudaStream_t s, uint32_t *zero = nullptr, uint32_t zero_words = 0);
+cudaError_t launch_build_tables(const uint8_t *freqs, uint32_t n_tables, uint32_t *tables, cudaStream_t s);
 // max_palette_bytes = max over the batch of GenTCHeader::palette_bytes (sizes the grid)
 // marks: NULL, or kLaunchesPerBatch + 1 events recorded around every kernel (profiling)
 cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,

@@ -166,6 +166,11 @@ int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *
 int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, void *out_host,
                            uint32_t flags, uint64_t *ticket);
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev);
+/* The player's main loop (demo/demo.cpp:504-600) over n frames already in host memory: frame f is submitted with
+ * gst_streamer_submit_ex (out_dev / out_host, when not NULL, advance by one decoded frame per f) and waited for
+ * depth - 1 submissions later; returns when every frame is done. */
+int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size_t *lens, uint32_t n,
+                      void *out_dev, void *out_host, uint32_t flags);
 void gst_streamer_destroy(gst_streamer *st);
 
 /* ---- stage taps for the parity tests (not used in production).  Any pointer may be NULL.
