@@ -126,12 +126,18 @@ def load_streams(cfg_id, width, height, distinct, rank, world):
     SURVEY.md section 8d).  Rank 0 encodes what the cache lacks; the others wait."""
     import gst_fixtures as fx
     seeds = [cfg_id * 10000 + i for i in range(distinct)]
+    if cfg_id == 4:
+        # the motion sequence: one base image translated by 2 px per frame; `distinct` consecutive frames, played
+        # forwards and backwards to fill the 600 (the encoder is ~1.2 s per frame and core)
+        make = lambda: fx.encode_motion(width, height, cfg_id * 10000, distinct)
+    else:
+        make = lambda: fx.encode_images(width, height, seeds)
     if world > 1:
         import torch.distributed as dist
         if rank == 0:
-            fx.encode_images(width, height, seeds)
+            make()
         dist.barrier()
-    streams = fx.encode_images(width, height, seeds)
+    streams = make()
     return [g for g, _ in streams], [d for _, d in streams]
 
 
@@ -237,7 +243,12 @@ def main():
     # image / frame i goes to rank i mod N, no data-path collective.  --scaling weak makes every
     # rank decode the whole configured batch instead (N independent replicas).
     strong = args.scaling == "strong"
-    order = [i % distinct for i in (shard_indices(images_total, rank, world) if strong else range(images_total))]
+    if args.config == 4 and distinct > 1:
+        period = 2 * distinct - 2  # frame f of the sequence: 0, 1, .., distinct-1, distinct-2, .., 1, 0, 1, ..
+        pick = lambda i: (i % period) if (i % period) < distinct else period - (i % period)
+    else:
+        pick = lambda i: i % distinct
+    order = [pick(i) for i in (shard_indices(images_total, rank, world) if strong else range(images_total))]
     if not strong:
         order = [(j + rank) % distinct for j in order]  # replicas start at different images
     images = len(order)
@@ -347,8 +358,8 @@ def main():
     # ---- the other scaling mode, for the record (N > 1 only) --------------------------------------
     other = None
     if world > 1:
-        o_order = ([(i + rank) % distinct for i in range(images_total)] if strong
-                   else [i % distinct for i in shard_indices(images_total, rank, world)])
+        o_order = ([(pick(i) + rank) % distinct for i in range(images_total)] if strong
+                   else [pick(i) for i in shard_indices(images_total, rank, world)])
         if o_order:
             o_res = Resident([files[j] for j in o_order])
             for _ in range(3):

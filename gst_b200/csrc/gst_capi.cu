@@ -341,6 +341,22 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   return GST_OK;
 }
 
+// the context's workspace for the standalone rANS entry points (caller holds ctx->ans_mutex)
+int ans_workspace(gst_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->ans_ws_cap) return GST_OK;
+  if (ctx->ans_ws) {
+    cudaStreamSynchronize(ctx->streams[0]);
+    cudaFree(ctx->ans_ws);
+    ctx->ans_ws = nullptr;
+    ctx->ans_ws_cap = 0;
+  }
+  const size_t cap = align_up(bytes + bytes / 4, 1 << 16);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->ans_ws), cap);
+  if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+  ctx->ans_ws_cap = cap;
+  return GST_OK;
+}
+
 // ans::GenerateHistogram (ans/histogram.cpp:41-123), restated: scale counts to sum M with
 // the float rounding rule of the reference, then fix the residual one unit at a time on the
 // symbol whose code-length cost changes least (min-heap on the rank).
@@ -1072,17 +1088,24 @@ int gst_ans_encode_stream(gst_ctx *ctx, const uint8_t *symbols, size_t n_symbols
   const uint32_t groups = static_cast<uint32_t>(n_symbols / gst::kGroupSyms);
   DeviceGuard guard(ctx->device);
   cudaStream_t s = ctx->streams[0];
-  uint8_t *d_sym = nullptr, *d_scratch = nullptr, *d_out = nullptr;
-  uint16_t *d_f = nullptr;
-  uint32_t *d_sizes = nullptr, *d_offsets = nullptr;
+  // one grow-only device workspace per context, carved up per call (no allocation in steady state):
+  // [symbols][per-group scratch][freqs 512][sizes][offsets][output stream (bound)]
+  std::lock_guard<std::mutex> ws_lock(ctx->ans_mutex);
+  const size_t o_sym = 0;
+  const size_t o_scr = o_sym + align_up(n_symbols, 256);
+  const size_t o_f = o_scr + align_up(static_cast<size_t>(groups) * gst::kEncGroupCapBytes, 256);
+  const size_t o_sizes = o_f + 512;
+  const size_t o_offs = o_sizes + align_up(4 * static_cast<size_t>(groups), 256);
+  const size_t o_out = o_offs + align_up(4 * static_cast<size_t>(groups), 256);
+  const size_t ws_bytes = o_out + align_up(gst_ans_encode_bound(n_symbols), 256);
+  int rc2 = ans_workspace(ctx, ws_bytes);
+  if (rc2) return rc2;
+  uint8_t *d_sym = ctx->ans_ws + o_sym, *d_scratch = ctx->ans_ws + o_scr, *d_out = ctx->ans_ws + o_out;
+  uint16_t *d_f = reinterpret_cast<uint16_t *>(ctx->ans_ws + o_f);
+  uint32_t *d_sizes = reinterpret_cast<uint32_t *>(ctx->ans_ws + o_sizes), *d_offsets = reinterpret_cast<uint32_t *>(ctx->ans_ws + o_offs);
   std::vector<uint32_t> sizes(groups), offsets(groups);
   size_t total = 0;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_sym), n_symbols);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_scratch), static_cast<size_t>(groups) * gst::kEncGroupCapBytes);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_f), sizeof f16);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_sizes), 4 * static_cast<size_t>(groups));
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_offsets), 4 * static_cast<size_t>(groups));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_sym, symbols, n_symbols, cudaMemcpyHostToDevice, s);
+  cudaError_t e = cudaMemcpyAsync(d_sym, symbols, n_symbols, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, f16, sizeof f16, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = gst::launch_ans_encode(d_sym, groups, d_f, d_scratch, d_sizes, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(sizes.data(), d_sizes, 4 * static_cast<size_t>(groups), cudaMemcpyDeviceToHost, s);
@@ -1095,19 +1118,13 @@ int gst_ans_encode_stream(gst_ctx *ctx, const uint8_t *symbols, size_t n_symbols
       offsets[g] = static_cast<uint32_t>(cum);
     }
     total = (cum + 3) & ~static_cast<size_t>(3);
-    if (total > stream_cap) {
-      cudaFree(d_sym); cudaFree(d_scratch); cudaFree(d_f); cudaFree(d_sizes); cudaFree(d_offsets);
-      return fail(GST_ERR_INVALID, "stream_out holds %zu bytes, the stream needs %zu", stream_cap, total);
-    }
-    e = cudaMalloc(reinterpret_cast<void **>(&d_out), total);
+    if (total > stream_cap) return fail(GST_ERR_INVALID, "stream_out holds %zu bytes, the stream needs %zu", stream_cap, total);
+    e = cudaMemsetAsync(d_out, 0, total, s);
   }
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, total, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, offsets.data(), 4 * static_cast<size_t>(groups), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = gst::launch_ans_encode_gather(d_scratch, d_sizes, d_offsets, groups, d_out, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(stream_out, d_out, total, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d_sym); cudaFree(d_scratch); cudaFree(d_f); cudaFree(d_sizes); cudaFree(d_offsets);
-  if (d_out) cudaFree(d_out);
   if (e != cudaSuccess) return fail(GST_ERR_CUDA, "ans encode failed: %s", cudaGetErrorString(e));
   *stream_bytes = total;
   return GST_OK;
@@ -1193,17 +1210,16 @@ int gst_ans_decode(gst_ans_decoder *d, uint32_t lanes, const uint32_t *states, c
   }
   DeviceGuard guard(d->ctx->device);
   cudaStream_t s = d->ctx->streams[0];
-  const size_t slack = 0;
-  uint8_t *dbuf = nullptr, *dout = nullptr;
   const size_t out_bytes = static_cast<size_t>(groups) * lanes * gst::kSymsPerLane;
-  GST_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&dbuf), slack + total));
-  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dout), out_bytes);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dbuf + slack, host.data(), total, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = gst::launch_ans_decode_plain(d->table, dbuf + slack, total, groups, lanes, dout, s);
+  std::lock_guard<std::mutex> ws_lock(d->ctx->ans_mutex);  // the context's grow-only workspace: [input][output]
+  const size_t o_out = align_up(total, 256);
+  int rc = ans_workspace(d->ctx, o_out + out_bytes);
+  if (rc) return rc;
+  uint8_t *dbuf = d->ctx->ans_ws, *dout = d->ctx->ans_ws + o_out;
+  cudaError_t e = cudaMemcpyAsync(dbuf, host.data(), total, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = gst::launch_ans_decode_plain(d->table, dbuf, total, groups, lanes, dout, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(dbuf);
-  if (dout) cudaFree(dout);
   if (e != cudaSuccess) return fail(GST_ERR_CUDA, "ans decode failed: %s", cudaGetErrorString(e));
   return GST_OK;
 }

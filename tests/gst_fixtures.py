@@ -158,12 +158,20 @@ def matches_golden(out, golden):
     return bool(np.array_equal(out, golden))
 
 
-def encode_image(width, height, seed, noise_only=False):
+def _tag(width, height, seed, noise_only=False, shift=None):
+    if shift is not None:
+        return f"motion_{width}x{height}_s{seed}_x{shift}"
+    return f"{'noise' if noise_only else 'synth'}_{width}x{height}_s{seed}"
+
+
+def encode_image(width, height, seed, noise_only=False, shift=None):
     """Seeded synthetic image through the reference encoder, cached on disk.  Returns
     (.gst bytes, golden) where golden is the encoder's PhysicalBlocks() as a uint8 array, or,
-    for images above 1 Mpixel, its GoldenSha (keeps the cache that travels to the GPU box small)."""
+    for images above 1 Mpixel, its GoldenSha (keeps the cache that travels to the GPU box small).
+    shift: the image translated horizontally by `shift` pixels (wrapping) -- a frame of the motion
+    sequence of SURVEY.md section 8(d)."""
     os.makedirs(CACHE_DIR, exist_ok=True)
-    tag = f"{'noise' if noise_only else 'synth'}_{width}x{height}_s{seed}"
+    tag = _tag(width, height, seed, noise_only, shift)
     pg, pd, ps = (os.path.join(CACHE_DIR, tag + ext) for ext in (".gst", ".dxt", ".sha"))
     big = width * height > BIG_PIXELS
     if os.path.exists(pg) and os.path.exists(ps if big else pd):
@@ -173,6 +181,8 @@ def encode_image(width, height, seed, noise_only=False):
         img = np.random.default_rng(seed).integers(0, 256, size=(height, width, 3), dtype=np.uint8)
     else:
         img = synth_image(width, height, seed)
+        if shift:
+            img = np.ascontiguousarray(np.roll(img, shift, axis=1))
     gst, dxt = encode_rgb(img)
     gst.tofile(pg + ".tmp")
     os.replace(pg + ".tmp", pg)
@@ -206,6 +216,28 @@ def encode_images(width, height, seeds, workers=None):
             if pr.wait() != 0:
                 raise RuntimeError("fixture encoder worker failed")
     return [encode_image(width, height, s) for s in seeds]
+
+
+def encode_motion(width, height, seed, n_frames, step=2, workers=None):
+    """Frames 0 .. n_frames-1 of the motion sequence: the seeded base image translated by `step` pixels per frame
+    (SURVEY.md section 8d), each through the reference encoder; missing ones on parallel worker processes."""
+    ext = ".sha" if width * height > BIG_PIXELS else ".dxt"
+    shifts = [k * step for k in range(n_frames)]
+    missing = [x for x in shifts if not (os.path.exists(os.path.join(CACHE_DIR, _tag(width, height, seed, shift=x) + ".gst")) and
+                                         os.path.exists(os.path.join(CACHE_DIR, _tag(width, height, seed, shift=x) + ext)))]
+    if len(missing) > 1:
+        import sys
+        workers = workers or min(len(missing), os.cpu_count() or 1)
+        procs = []
+        for k in range(workers):
+            part = missing[k::workers]
+            if part:
+                procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--encode-motion", str(width),
+                                               str(height), str(seed)] + [str(x) for x in part]))
+        for pr in procs:
+            if pr.wait() != 0:
+                raise RuntimeError("fixture encoder worker failed")
+    return [encode_image(width, height, seed, shift=x) for x in shifts]
 
 
 def golden_test1():
@@ -357,3 +389,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 4 and sys.argv[1] == "--encode":
         for seed in sys.argv[4:]:
             encode_image(int(sys.argv[2]), int(sys.argv[3]), int(seed))
+    if len(sys.argv) > 5 and sys.argv[1] == "--encode-motion":
+        for x in sys.argv[5:]:
+            encode_image(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), shift=int(x))
