@@ -88,6 +88,8 @@ struct gst_ctx {
     uint8_t *d_in = nullptr, *d_out = nullptr;
     size_t cap_in = 0, cap_out = 0;
   } host_slots[kHostSlots];
+  // [0]: status flags the kernels OR into (gst_status_flags), [1]: a zero word
+  uint32_t *d_status = nullptr;
   // workspace of the standalone rANS decode / encode entry points (grow-only, one call at a time)
   std::mutex ans_mutex;
   uint8_t *ans_ws = nullptr;
@@ -295,6 +297,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.idx_total = reinterpret_cast<int32_t *>(scratch + L.total_off);
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
+  p.status = ctx->d_status;
   gst::fill_kernel_constants(&p);
   if (inline_offsets) {
     if (n != 1) return fail(GST_ERR_INVALID, "inline offsets need a single image");
@@ -449,6 +452,12 @@ int gst_ctx_create(int device, gst_ctx **out) {
       return fail(GST_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
   }
+  e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_status), 16);
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, 16);
+  if (e != cudaSuccess) {
+    gst_ctx_destroy(ctx);
+    return fail(GST_ERR_CUDA, "status word allocation failed: %s", cudaGetErrorString(e));
+  }
   // keep freed scratch in the pool so per-call cudaMallocAsync does not hit the OS
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -476,6 +485,7 @@ void gst_ctx_destroy(gst_ctx *ctx) {
   for (auto &kv : ctx->stream_scratch)
     if (kv.second && kv.second->ptr) cudaFree(kv.second->ptr);
   if (ctx->ans_ws) cudaFree(ctx->ans_ws);
+  if (ctx->d_status) cudaFree(ctx->d_status);
   for (auto &hs : ctx->host_slots) {
     for (int k = 0; k < 2; ++k) {
       if (hs.pinned[k]) cudaFreeHost(hs.pinned[k]);
@@ -1230,6 +1240,14 @@ void gst_ans_destroy(gst_ans_decoder *d) {
   if (d->table) cudaFree(d->table);
   if (d->freqs) cudaFree(d->freqs);
   delete d;
+}
+
+int gst_status_flags(gst_ctx *ctx, uint32_t *flags, int clear) {
+  if (!ctx || !flags) return fail(GST_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  GST_CUDA_TRY(cudaMemcpy(flags, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (clear && *flags) GST_CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
+  return GST_OK;
 }
 
 int gst_launches_per_batch(void) { return gst::kLaunchesPerBatch; }

@@ -19,6 +19,8 @@
 // All arithmetic is integer and follows the reference bit for bit: wrapping u32 rANS
 // state, C truncating division in the 5/3 lifting and in YCoCg->RGB, (char) truncation of
 // the wavelet output, unmasked shift/or 565 pack.
+#include <type_traits>
+
 #include "gst_kernels.cuh"
 
 namespace gst {
@@ -396,8 +398,8 @@ __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__res
 //   index groups: symbols are (delta + 128) per DXT block in raster order
 //       (codec/dxt_image.cpp:610-618) and every lane owns 256 consecutive blocks (a "run").
 //       Stage 3 (codec/decode_indices.cl:24, idx[i] = sum_{j<=i} d[j]) is fused behind the
-//       decoder: symbols arrive last-to-first, so the lane writes S[i] = sum of the deltas AFTER
-//       i inside its run, and idx[i] = run_end[run] - S[i], where run_end is the inclusive
+//       decoder: symbols arrive last-to-first, so the lane writes S[i] = MINUS the sum of the deltas AFTER
+//       i inside its run, and idx[i] = run_end[run] + S[i], where run_end is the inclusive
 //       prefix at the end of the run (group-local here, the carry of the earlier groups is added by
 //       wavelet_assemble_kernel).  S is stored mod 2^16
 //       when every palette of the batch has <= 65536 entries (idx < 2^16 then makes the 16-bit
@@ -507,7 +509,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
     return;
   }
 
-  uint32_t sum[NC];  // sum of (byte - 128) over the symbols decoded so far = positions after the current one
+  uint32_t sum[NC];  // MINUS the sum of (byte - 128) over the symbols decoded so far = the positions after the current one
 #pragma unroll
   for (int c = 0; c < NC; ++c) sum[c] = 0;
   const size_t t0 = static_cast<size_t>(b) * p.n_blocks + static_cast<size_t>(group) * kGroupSyms + 15 * 512 + lane * 16;
@@ -524,7 +526,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
 #pragma unroll
                                    for (int i = 15; i >= 0; --i) {
                                      s[i] = sum[c];
-                                     sum[c] += ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) - 128u;
+                                     sum[c] += 128u - ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
                                    }
                                    if (idx16) {
                                      uint32_t q[8];
@@ -545,7 +547,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
   // totals of the earlier groups of the image (the cross-group part of stage 3, codec/decode_indices.cl:66-84)
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    uint32_t inc = sum[c];
+    uint32_t inc = 0u - sum[c];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
@@ -851,19 +853,20 @@ constexpr int kBY = 1024, kBO = 0, kBG = 512;
 constexpr int kB1 = 512;                             // bias of the dividend -cg
 constexpr int kB2 = 256 + kBY - kBO;                 // bias of the dividend t - co
 constexpr int kBiasG = 256 + kBG + kBY + kB1 / 2;    // g + kBiasG: a multiple of 2048, so that (g + bias) << 5 only spills into masked bits
-constexpr int kBiasR = 32768 + 128 + kBO;            // r + kBiasR: a multiple of 32
+constexpr int kBiasB = kB2 / 2;                      // b + kBiasB
+constexpr int kBiasR = kBiasB + 128 + kBO;           // r + kBiasR: a multiple of 32
 static_assert(kBiasG % 2048 == 0 && kBiasR % 32 == 0 && kB2 % 2 == 0 && kB2 >= 512, "colour conversion biases");
 // codec/assemble.cl:39-62 for both endpoints at once: YCoCg667 -> RGB565 with truncating division and
 // an unmasked shift/or pack.  Inputs: (int8 value + 128) of plane A | plane B << 16.
 //   t = y - cg / 2;  g = cg + t;  b = (t - co) / 2;  r = b + co;  out = r << 11 | g << 5 | b  (low 16 bits)
-// Outputs (per half): R = r + kBiasR, G = g + kBiasG, Bq = b + 32768.
+// Outputs (per half): R = r + kBiasR, G = g + kBiasG, Bq = b + kBiasB.
 __device__ __forceinline__ void ycocg_to_rgb_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk, uint32_t &R, uint32_t &G,
                                                uint32_t &Bq) {
   const uint32_t Tn = fma_sub_from(CG, pk(kB1 + 128 + kBG));          // -cg + kB1; trunc(-cg / 2) = -trunc(cg / 2)
   const uint32_t Tb = shr_add<1>(trunc_fix<1, kB1>(Tn, sk) & 0xFFFEFFFEu, Y);   // t + kB1 / 2 + 128 + kBY
   G = fma_add(CG, Tb);                                                // g + kBiasG
   const uint32_t V = fma_sub_from(CO, Tb);                            // (t - co) + kB2
-  Bq = shr_add<1>(trunc_fix<1, kB2>(V, sk) & 0xFFFEFFFEu, pk(32768 - kB2 / 2));  // b + 32768
+  Bq = (trunc_fix<1, kB2>(V, sk) & 0xFFFEFFFEu) >> 1;                  // b + kB2 / 2
   R = fma_add(Bq, CO);                                                // r + kBiasR
 }
 __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t CG, const ShiftK &sk) {  // ep1 | ep2 << 16
@@ -872,7 +875,11 @@ __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t 
   uint32_t rs, gs;
   asm("mul.lo.u32 %0, %1, 2048;" : "=r"(rs) : "r"(R));  // << 11 and << 5 on the FMA pipe
   asm("mul.lo.u32 %0, %1, 32;" : "=r"(gs) : "r"(G));
-  return (rs & 0xF800F800u) | (gs & 0xFFE0FFE0u) | (Bq ^ 0x80008000u);
+  // b mod 2^16 in each half: a per-half add (VIADD.16x2, FMA pipe) takes the bias off without a borrow between
+  // the halves, so the three fields combine in two LOP3
+  uint32_t bx;
+  asm("add.s16x2 %0, %1, %2;" : "=r"(bx) : "r"(Bq), "r"(ph(-kBiasB)));
+  return (rs & 0xF800F800u) | ((gs & 0xFFE0FFE0u) | bx);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -929,8 +936,6 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   // out_off[4b..4b+3] of this image (codec/decoder.cpp:430-463): requested now, first used after the
   // lower wavelet levels, so the warp never waits for it
   const uint4 out_off = p.inline_off ? make_uint4(p.off8[0], p.off8[1], p.off8[2], p.off8[3]) : __ldg(reinterpret_cast<const uint4 *>(p.cmp) + b);
-  uint32_t n_entries = 0;
-  bool pal_ok = false;
   const uint32_t *pal = nullptr;
 
   // ---- assembly inputs of slab 0 start their trip now ---------------------------------
@@ -989,27 +994,47 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   // the suffix sums come from DRAM (the rANS kernel wrote them): pull them into L1 two slabs before
   // they are loaded, so that the load -> index -> palette gather chain of a slab starts on time
   auto prefetch_sfx = [&](const uint8_t *sp) { asm volatile("prefetch.global.L1 [%0];" ::"l"(sp)); };
-  // k = slab of these suffix sums
+  // k = slab of these suffix sums.  idx = min(run_end + S, n_entries - 1): with 16-bit sums two indices are one
+  // VIADDMNMX.U16x2 (add, wrap and clamp per half); `seen` keeps the largest unclamped index for the status flag.
+  uint32_t nmax = 0, seen = 0;  // n_entries - 1 (in both halves when IDX16)
   auto load_words = [&](const Sfx &sf, uint32_t k, uint32_t gidx, uint32_t (&word)[4]) {
     const uint32_t re = __shfl_sync(0xffffffffu, re_row, 4 * k + (lane >> 3));
     uint32_t idx[4];
-    if (IDX16) {  // idx = (re - S) mod 2^16; the other half of the word only reaches the bits that are masked off
-      idx[0] = (re - sf.raw.x) & 0xFFFFu; idx[1] = (re - (sf.raw.x >> 16)) & 0xFFFFu;
-      idx[2] = (re - sf.raw.y) & 0xFFFFu; idx[3] = (re - (sf.raw.y >> 16)) & 0xFFFFu;
+    if (IDX16) {
+      const uint32_t re2 = __byte_perm(re, 0u, 0x1010);  // run end mod 2^16 in both halves
+      const uint32_t p0 = __viaddmin_u16x2(re2, sf.raw.x, nmax), p1 = __viaddmin_u16x2(re2, sf.raw.y, nmax);
+      seen = __viaddmax_u16x2(re2, sf.raw.x, seen);
+      seen = __viaddmax_u16x2(re2, sf.raw.y, seen);
+      idx[0] = p0 & 0xFFFFu; idx[1] = p0 >> 16; idx[2] = p1 & 0xFFFFu; idx[3] = p1 >> 16;
     } else {
-      idx[0] = re - sf.raw.x; idx[1] = re - sf.raw.y; idx[2] = re - sf.raw.z; idx[3] = re - sf.raw.w;
+      const uint32_t u[4] = {re + sf.raw.x, re + sf.raw.y, re + sf.raw.z, re + sf.raw.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        seen = max(seen, u[j]);
+        idx[j] = min(u[j], nmax);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) word[j] = pal_ok ? __ldg(pal + min(idx[j], n_entries - 1)) : 0u;
-    if (TAP && p.tap_indices)
-      *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
+    for (int j = 0; j < 4; ++j) word[j] = __ldg(pal + idx[j]);
+    if (TAP && p.tap_indices) {  // the unclamped indices, as the reference computes them
+      uint32_t u[4];
+      if (IDX16) {
+        u[0] = (re + sf.raw.x) & 0xFFFFu; u[1] = (re + (sf.raw.x >> 16)) & 0xFFFFu;
+        u[2] = (re + sf.raw.y) & 0xFFFFu; u[3] = (re + (sf.raw.y >> 16)) & 0xFFFFu;
+      } else {
+        u[0] = re + sf.raw.x; u[1] = re + sf.raw.y; u[2] = re + sf.raw.z; u[3] = re + sf.raw.w;
+      }
+      *reinterpret_cast<uint4 *>(p.tap_indices + img_block0 + gidx) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
   };
   // software pipeline of the assembly inputs: the palette words of slab k + 1 are gathered while slab k
-  // is assembled, from suffix sums loaded two slabs earlier and prefetched into L1 two slabs before that
-  Sfx sa = load_sfx(gidx0), sb = load_sfx(gidx0 + slab_stride);
-  const uint8_t *pf_a = sfx_ptr(gidx0 + 2 * slab_stride), *pf_b = sfx_ptr(gidx0 + 3 * slab_stride);  // prefetched, not yet loaded
-  prefetch_sfx(pf_a);
-  prefetch_sfx(pf_b);
+  // is assembled, from suffix sums loaded two slabs earlier and prefetched into L1 two slabs before that.
+  // Slot (k + 1) & 1 of sfx / pf / words belongs to slab k + 1 (then k + 3, k + 5): with the slab loop unrolled
+  // by two nothing has to be moved from register to register.
+  Sfx sfx[2] = {load_sfx(gidx0), load_sfx(gidx0 + slab_stride)};
+  const uint8_t *pf[2] = {sfx_ptr(gidx0 + 2 * slab_stride), sfx_ptr(gidx0 + 3 * slab_stride)};  // prefetched, not yet loaded
+  prefetch_sfx(pf[0]);
+  prefetch_sfx(pf[1]);
 
   // ---- stage 4: inverse wavelet ------------------------------------------------------------
   uint32_t k10 = 0x10101010u;
@@ -1024,19 +1049,21 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   low_level_p<8>(w_s, lane, k10, sk);
   low_level_p<16>(w_s, lane, k10, sk);
 
-  uint32_t word_nx[4];  // palette words of the next slab
+  uint32_t words[2][4];  // palette words of slab k in words[k & 1]
   {  // slab 0: indices -> palette words;  slabs 1, 2: suffix sums in registers
     const uint32_t palette_bytes = out_off.w - out_off.z;
     const uint32_t pal_off = out_off.z - 7u * p.n_blocks * b - 6u * p.n_blocks;  // compact palette scratch
-    n_entries = palette_bytes / 4;
-    pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
-    pal = reinterpret_cast<const uint32_t *>(p.palette + (pal_ok ? pal_off : 0));
-    load_words(sa, 0, gidx0, word_nx);
-    sa = sb;
-    sb = load_sfx_at(pf_a);
-    pf_a = pf_b;
-    pf_b = sfx_ptr(gidx0 + 4 * slab_stride);
-    prefetch_sfx(pf_b);
+    const uint32_t n_entries = palette_bytes / 4;
+    // a palette outside the scratch (malformed offsets) or an empty one: every index reads the zero word, flag 2
+    const bool pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
+    pal = pal_ok ? reinterpret_cast<const uint32_t *>(p.palette + pal_off) : p.status + 1;
+    nmax = pal_ok ? n_entries - 1 : 0u;
+    if (!pal_ok && lane == 0) atomicOr(p.status, 2u);
+    if (IDX16) nmax = __byte_perm(nmax, 0u, 0x1010);
+    load_words(sfx[0], 0, gidx0, words[0]);
+    sfx[0] = load_sfx_at(pf[0]);
+    pf[0] = sfx_ptr(gidx0 + 4 * slab_stride);
+    prefetch_sfx(pf[0]);
   }
 
   // level 32, rows: lane = row
@@ -1079,17 +1106,15 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   __syncwarp();
 
   // ---- stage 5: assembly, codec/assemble.cl:64-129 ---------------------------------------
-#pragma unroll 1
-  for (uint32_t k = 0; k < 8; ++k) {
+  auto slab = [&](auto q_c, uint32_t k) {
+    constexpr int Q = decltype(q_c)::value;  // (k + 1) & 1
     const uint32_t gidx = gidx0 + k * slab_stride;
-    const uint32_t word[4] = {word_nx[0], word_nx[1], word_nx[2], word_nx[3]};
-    if (k + 1 < 8) load_words(sa, k + 1, gidx + slab_stride, word_nx);  // its S was loaded two slabs ago
-    sa = sb;
-    if (k + 3 < 8) sb = load_sfx_at(pf_a);
-    pf_a = pf_b;
+    const uint32_t (&word)[4] = words[Q ^ 1];
+    if (k + 1 < 8) load_words(sfx[Q], k + 1, gidx + slab_stride, words[Q]);  // its S was loaded two slabs ago
+    if (k + 3 < 8) sfx[Q] = load_sfx_at(pf[Q]);
     if (k + 5 < 8) {
-      pf_b = sfx_ptr(gidx + 5 * slab_stride);
-      prefetch_sfx(pf_b);
+      pf[Q] = sfx_ptr(gidx + 5 * slab_stride);
+      prefetch_sfx(pf[Q]);
     }
     // rows 4k..4k+3 of the tile, 4 blocks per lane: (int8 + 128) of plane A | plane B << 16
     const uint32_t src = wchunk(w_s, 4 * k + (lane >> 3), lane & 7);
@@ -1115,8 +1140,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
       for (int j = 0; j < 4; ++j) {
         uint32_t R, G, Bq;
         ycocg_to_rgb_p(Y[j], CO[j], CG[j], sk, R, G, Bq);
-        int c0[3] = {static_cast<int>(R & 0xFFFFu) - kBiasR, static_cast<int>(G & 0xFFFFu) - kBiasG, static_cast<int>(Bq & 0xFFFFu) - 32768};
-        int c1[3] = {static_cast<int>(R >> 16) - kBiasR, static_cast<int>(G >> 16) - kBiasG, static_cast<int>(Bq >> 16) - 32768};
+        int c0[3] = {static_cast<int>(R & 0xFFFFu) - kBiasR, static_cast<int>(G & 0xFFFFu) - kBiasG, static_cast<int>(Bq & 0xFFFFu) - kBiasB};
+        int c1[3] = {static_cast<int>(R >> 16) - kBiasR, static_cast<int>(G >> 16) - kBiasG, static_cast<int>(Bq >> 16) - kBiasB};
         c0[0] = static_cast<int>((static_cast<uint32_t>(c0[0]) << 3) | static_cast<uint32_t>(c0[0] >> 2));
         c0[1] = static_cast<int>((static_cast<uint32_t>(c0[1]) << 2) | static_cast<uint32_t>(c0[1] >> 4));
         c0[2] = static_cast<int>((static_cast<uint32_t>(c0[2]) << 3) | static_cast<uint32_t>(c0[2] >> 2));
@@ -1163,6 +1188,16 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
         st_global_cs_v4(dst + 32, wds[8], wds[9], wds[10], wds[11]);
       }
     }
+  };
+#pragma unroll 1
+  for (uint32_t k = 0; k < 8; k += 2) {
+    slab(std::integral_constant<int, 1>{}, k);
+    slab(std::integral_constant<int, 0>{}, k + 1);
+  }
+  // status: a palette index beyond the palette was clamped (a stream the reference encoder would not have written)
+  {
+    const bool over = IDX16 ? ((seen & 0xFFFFu) > (nmax & 0xFFFFu) || (seen >> 16) > (nmax >> 16)) : seen > nmax;
+    if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(p.status, 1u);
   }
 }
 

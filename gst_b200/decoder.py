@@ -276,6 +276,12 @@ class Decoder:
     # -- profiling -----------------------------------------------------------------------
     KERNEL_NAMES = ("build_tables", "rans_streams", "wavelet_assemble")
 
+    def status_flags(self, clear=True):
+        """gst_status_flags: bit 0 = a palette index was clamped, bit 1 = a palette region was out of range."""
+        f = C.c_uint32()
+        check(lib().gst_status_flags(self.ctx, C.byref(f), 1 if clear else 0))
+        return f.value
+
     def profile(self, on=True):
         check(lib().gst_profile_enable(self.ctx, 1 if on else 0))
 

@@ -173,6 +173,16 @@ int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size
                       void *out_dev, void *out_host, uint32_t flags);
 void gst_streamer_destroy(gst_streamer *st);
 
+/* ---- stream sanity flags.  The reference does not validate stream contents (malformed input is undefined behaviour,
+ * SURVEY.md section 5); here every access is clamped, and a decode that had to clamp says so: the kernels OR
+ *   GST_FLAG_INDEX_CLAMPED   a palette index lay beyond the image's palette (it was clamped to the last entry)
+ *   GST_FLAG_PALETTE_RANGE   an image's palette region did not fit its batch (its blocks got index word 0)
+ * into one word per context.  gst_status_flags reads it (and clears it when `clear` is non-zero); call it after the
+ * work of interest has completed (gst_stream_sync / an event). */
+#define GST_FLAG_INDEX_CLAMPED 1u
+#define GST_FLAG_PALETTE_RANGE 2u
+int gst_status_flags(gst_ctx *ctx, uint32_t *flags, int clear);
+
 /* ---- stage taps for the parity tests (not used in production).  Any pointer may be NULL.
  *   symbols_dev : sum(7N + P) bytes, reference decmp_buf layout (codec/decoder.cpp:212)
  *   planes_dev  : n*6N int8, raster planes (codec/decoder.cpp:280)

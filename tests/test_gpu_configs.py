@@ -158,3 +158,25 @@ def test_launch_count_small_and_large_calls(decoder):
     assert lib().gst_launches_for_batch(one, 1) == 2      # tables built by the consuming CTAs
     assert lib().gst_launches_for_batch(many, 32) == 3
     assert lib().gst_launches_per_batch() == 3
+
+
+def test_status_flag_reports_clamped_palette_indices(decoder):
+    """A stream whose index deltas walk past the end of its palette (the reference would read out of bounds): the
+    decode is memory-safe, and gst_status_flags says that an index was clamped; a well-formed stream sets nothing."""
+    w = h = 512
+    n = (w // 4) * (h // 4)
+    rng = np.random.default_rng(5)
+    planes = np.clip(np.rint(rng.laplace(0.0, 4.0, size=6 * n)) + 128, 0, 255).astype(np.uint8)
+    palette = rng.integers(0, 256, size=8192, dtype=np.uint8)          # 2048 entries
+    good = np.full(n, 128, dtype=np.uint8)                              # every delta 0: index 0 everywhere
+    bad = np.full(n, 128 + 100, dtype=np.uint8)                         # +100 per block: far beyond 2048 entries
+    decoder.status_flags(clear=True)
+    out = decoder.DecompressDXT(gst_b200.build_gst(decoder, w, h, planes[: 2 * n], planes[2 * n:], palette, good))
+    assert decoder.status_flags() == 0
+    assert np.array_equal(out.view("<u4")[1::2], np.full(n, palette.view("<u4")[0]))
+    out = decoder.DecompressDXT(gst_b200.build_gst(decoder, w, h, planes[: 2 * n], planes[2 * n:], palette, bad))
+    assert decoder.status_flags(clear=True) & 1
+    assert decoder.status_flags() == 0
+    # block 30 has index 31 * 100 = 3100 > 2047: it carries the last palette entry
+    assert out.view("<u4")[1::2][30] == palette.view("<u4")[-1]
+    assert out.view("<u4")[1::2][10] == palette.view("<u4")[1100]
