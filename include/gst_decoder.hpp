@@ -143,11 +143,18 @@ inline gst_event Load(const std::unique_ptr<gpu::GPUContext> &ctx, const GenTCHe
 }  // namespace detail
 
 // codec/decoder.h:15-36 -------------------------------------------------------------------
+// The reference compiles its seven kernels here and checks the device's work-group limits
+// (codec/decoder.cpp:558-591).  The CUDA kernels are compiled ahead of time for sm_100a and gst_ctx_create has
+// already refused any other device, so a context that exists is a context that can decode.
 inline bool InitializeDecoder(const std::unique_ptr<gpu::GPUContext> &gpu_ctx) { return gpu_ctx != nullptr; }
 
 inline DXTImage DecompressDXT(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, const std::vector<uint8_t> &cmp_data) {
+  // validate before anything is sized from the header (a short or corrupt buffer must not be read past its end
+  // or drive a huge allocation)
+  gst_header h;
+  if (gst_parse_header(cmp_data.data(), cmp_data.size(), &h) != GST_OK) throw std::runtime_error(gst_last_error());
   GenTCHeader hdr;
-  hdr.LoadFrom(cmp_data.data());
+  std::memcpy(&hdr, &h, sizeof(hdr));
   std::vector<uint8_t> out(static_cast<size_t>(hdr.width) * hdr.height / 2, 0xFF);
   if (gst_decompress_host(gpu_ctx->Handle(), cmp_data.data(), cmp_data.size(), 0, out.data(), out.size()) != GST_OK)
     throw std::runtime_error(gst_last_error());
@@ -175,12 +182,27 @@ inline gst_event LoadRGBs(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, const
 
 inline size_t RequiredScratchMem(const GenTCHeader &hdr) { return gst_required_scratch(detail::AsC(&hdr)); }
 
-// The reference keeps one process-wide arena (codec/decoder.cpp:96 gPreloader); here it lives
-// in the context that is passed in, and FreeDecompressor needs that context.
+// The reference keeps one process-wide arena (codec/decoder.cpp:96 gPreloader).  Here the arena lives in the
+// context; the facade remembers the context PreallocateDecompressor was last called on, so that the reference's
+// argument-less FreeDecompressor() (codec/decoder.h:37) works as written.  The context must still be alive.
+namespace detail {
+inline gst_ctx *&PreloadedContext() {
+  static gst_ctx *ctx = nullptr;
+  return ctx;
+}
+}  // namespace detail
 inline void PreallocateDecompressor(const std::unique_ptr<gpu::GPUContext> &gpu_ctx, size_t req_sz) {
   if (gst_preallocate(gpu_ctx->Handle(), req_sz) != GST_OK) throw std::runtime_error(gst_last_error());
+  detail::PreloadedContext() = gpu_ctx->Handle();
 }
-inline void FreeDecompressor(const std::unique_ptr<gpu::GPUContext> &gpu_ctx) { gst_free_scratch(gpu_ctx->Handle()); }
+inline void FreeDecompressor() {
+  if (detail::PreloadedContext()) gst_free_scratch(detail::PreloadedContext());
+  detail::PreloadedContext() = nullptr;
+}
+inline void FreeDecompressor(const std::unique_ptr<gpu::GPUContext> &gpu_ctx) {
+  gst_free_scratch(gpu_ctx->Handle());
+  if (detail::PreloadedContext() == gpu_ctx->Handle()) detail::PreloadedContext() = nullptr;
+}
 
 // UploadData (codec/decoder.cpp:430-476): one .gst file -> the device buffer LoadCompressedDXT
 // expects (8 offsets at byte 0, file minus header at byte 512).

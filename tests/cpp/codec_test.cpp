@@ -83,7 +83,7 @@ int main(int argc, char **argv) {
     ctx->ReadBuffer(q, out, i * golden.size(), host.data(), host.size(), true);
     EXPECT(host == golden);
   }
-  GenTC::FreeDecompressor(ctx);
+  GenTC::FreeDecompressor();  // the reference's argument-less form (codec/decoder.h:37)
 
   // the photos_sf page loop as one call (host files -> device textures), ragged last page
   {

@@ -36,6 +36,12 @@ def test_cpp_facade_builds_and_fails_loudly_without_gpu():
     assert r.returncode == 3 and "no CPU fallback" in r.stderr
 
 
+def test_facade_keeps_the_reference_signatures():
+    """tests/cpp/signature_check.cpp: every codec/decoder.h declaration, verbatim, binds to the facade."""
+    src = os.path.join(fx.ROOT, "tests", "cpp", "signature_check.cpp")
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-fsyntax-only", "-I", os.path.join(fx.ROOT, "include"), src])
+
+
 @pytest.mark.gpu
 def test_cpp_codec_test():
     exe = _build()
