@@ -7,7 +7,7 @@
  * reference's OpenCL kernels so that every CUDA stage can be checked in
  * isolation.  Citations are relative to /root/reference.
  *
- * PARITY IS PINNED (not "parity unpinned"): tests/test_oracle_vs_reference.py
+ * PARITY IS PINNED (not "parity unpinned"): tests/test_oracle.py
  * checks this file against
  *   - the reference's own encoder output PhysicalBlocks() on codec/test/test1.png
  *     (the identity of codec/test/codec_test.cpp:36-48), via tests/golden/,
