@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="strong",
                     help="strong (default): the configured batch is the job, image / frame i goes to rank i mod N; "
                          "weak: every GPU decodes the whole configured batch")
+    ap.add_argument("--direct-upload", action="store_true",
+                    help="e2e legs: DMA every pinned .gst file from where it lies instead of packing pages (gst_ctx_set_direct_upload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample")
@@ -237,6 +239,8 @@ def main():
     from gst_b200.shard import reduce_job, shard_indices
 
     dec = gst_b200.Decoder(local_rank)
+    if args.direct_upload:
+        check(lib().gst_ctx_set_direct_upload(dec.ctx, 1))
     distinct = min(args.distinct, images_total)
     files, goldens = load_streams(args.config, width, height, distinct, rank, world)
     # The job is the configured batch (BASELINE.json: "sharded across 1/2/4/8 B200", frames "streamed across 8 B200"):

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "gst_ans_encode_bound": (_sz, [_sz]),
     "gst_ans_encode_stream": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "gst_build_tables": (_int, [_vp, _vp, _vp, _u32, _vp]),
+    "gst_ctx_set_direct_upload": (_int, [_vp, _int]),
     "gst_status_flags": (_int, [_vp, C.POINTER(_u32), _int]),
     "gst_launches_per_batch": (_int, []),
     "gst_launches_for_batch": (_int, [_hdr_p, _u32]),

@@ -88,6 +88,7 @@ struct gst_ctx {
     uint8_t *d_in = nullptr, *d_out = nullptr;
     size_t cap_in = 0, cap_out = 0;
   } host_slots[kHostSlots];
+  std::atomic<bool> direct_upload{false};  // gst_ctx_set_direct_upload
   // [0]: status flags the kernels OR into (gst_status_flags), [1]: a zero word
   uint32_t *d_status = nullptr;
   // workspace of the standalone rANS decode / encode entry points (grow-only, one call at a time)
@@ -229,7 +230,7 @@ struct Taps {
 // offsets travel in the kernel parameters (the frame streamer uploads a file as it lies)
 int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t stream, const void *cmp_dev,
                  size_t cmp_bytes, void *out_dev, int rgb, const Taps &taps, void *const *wait_events,
-                 uint32_t n_wait, void **done_event, bool inline_offsets = false) {
+                 uint32_t n_wait, void **done_event, bool inline_offsets = false, bool freq_inline = false) {
   if (!ctx) return fail(GST_ERR_INVALID, "null context");
   if (!cmp_dev || !out_dev) return fail(GST_ERR_INVALID, "null device buffer");
   BatchLayout L;
@@ -299,6 +300,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.out = static_cast<uint8_t *>(out_dev);
   p.status = ctx->d_status;
   gst::fill_kernel_constants(&p);
+  p.freq_inline = freq_inline ? 1u : 0u;
   if (inline_offsets) {
     if (n != 1) return fail(GST_ERR_INVALID, "inline offsets need a single image");
     const uint32_t N = L.n_blocks;
@@ -744,11 +746,11 @@ int gst_load_dxt_batch_tapped(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, 
                       nullptr);
 }
 
-// Host-to-host batch decode.  The batch is cut into pages (demo/photos_sf.cpp:688); page k is
-// handled by work stream k % 4 and by one host thread per stream: the thread packs the page
-// into pinned staging (two buffers per stream, so packing page k+4 overlaps the transfers of
-// page k), then enqueues H2D -> decode -> D2H on its stream.  Staging lives in the context
-// and only grows.
+// Host-to-host batch decode.  The batch is cut into pages (demo/photos_sf.cpp:688); a page is handled by one host
+// thread with a staging slot and stream drawn from the context's pool: the thread writes the page's offset table,
+// uploads every file in one copy (straight from the caller's buffer when that is pinned, through the slot's pinned
+// staging otherwise -- two buffers per slot, so staging page k+1 overlaps the transfers of page k), then enqueues
+// decode -> D2H on its stream.  Staging lives in the context and only grows.
 namespace {
 int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens, uint32_t n, uint32_t page, int mode,
                uint8_t *out, size_t out_cap, bool out_on_device);
@@ -850,18 +852,30 @@ int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens
       // the previous upload out of this staging buffer must have left the host
       e = cudaEventSynchronize(s.h2d_done[j]);
       if (e != cudaSuccess) return bail(GST_ERR_CUDA, "staging wait failed", e);
-      // pack the page into the pinned staging buffer (demo/photos_sf.cpp:753-806), one H2D copy.
-      // (DMA-ing every file from where it lies -- two copies per image -- was measured slower: the
-      // per-copy cost outweighs the saved host memcpy.)
+      // The page on the device (demo/photos_sf.cpp:753-806 packs [offsets][all frequency blocks][all payloads]; here
+      // the frequency blocks stay in front of their image's streams -- BatchParams::freq_inline -- so that a file is
+      // ONE copy): [out_off[4n]][in_off[4n]] padded to 512 | file 0 minus its header | file 1 minus its header ...
+      // By default the files are copied into the slot's pinned staging and the page goes up in one DMA (on one GPU
+      // 1024 copies of 640 KB cost more in per-copy latency than the packing pass they save: -4 % host to host,
+      // -10 % host to device).  With gst_ctx_set_direct_upload a pinned file is DMA-ed from where it lies and the
+      // host writes only the offsets region -- for boxes whose host memory, not the link, is the bottleneck.
+      for (uint32_t i = 0; i < cnt; ++i) {
+        int prc = gst_parse_header(gst_files[first + i], lens[first + i], &hdrs[i]);
+        if (prc) {
+          slot_rc[si] = prc;
+          slot_err[si] = g_err;
+          return;
+        }
+      }
       BatchLayout L;
-      int prc = pack_impl(gst_files + first, lens + first, cnt, s.pinned[j], s.cap_in, hdrs.data(), true, &L);
+      int prc = layout_batch(hdrs.data(), cnt, &L);
       if (prc) {
         slot_rc[si] = prc;
         slot_err[si] = g_err;
         return;
       }
       // the output stride and the staging were sized from the first file of the call: every page must match it
-      // (inside a page pack_impl has already checked the images against each other)
+      // (inside a page layout_batch has already checked the images against each other)
       if (hdrs[0].width != h0.width || hdrs[0].height != h0.height) {
         slot_rc[si] = GST_ERR_INVALID;
         char msg[160];
@@ -871,13 +885,60 @@ int host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens
         cudaStreamSynchronize(stream);
         return;
       }
-      e = cudaMemcpyAsync(s.d_in, s.pinned[j], L.total_cmp, cudaMemcpyHostToDevice, stream);
+      uint8_t *stage = s.pinned[j];
+      uint32_t *out_off = reinterpret_cast<uint32_t *>(stage), *in_off = out_off + 4 * cnt;
+      memset(stage, 0, L.off_region);
+      uint32_t in_acc = 0, out_acc = 0;
+      std::vector<uint32_t> base(cnt);
+      for (uint32_t i = 0; i < cnt; ++i) {
+        const gst_header &h = hdrs[i];
+        const uint32_t in_sz[4] = {h.y_cmp_sz, h.chroma_cmp_sz, h.palette_sz, h.indices_sz};
+        const uint32_t out_sz[4] = {2 * L.n_blocks, 4 * L.n_blocks, h.palette_bytes, L.n_blocks};
+        base[i] = in_acc;
+        in_acc += 2048;  // the image's four frequency blocks
+        for (int k = 0; k < 4; ++k) {
+          in_off[4 * i + k] = in_acc;
+          out_off[4 * i + k] = out_acc;
+          in_acc += in_sz[k];
+          out_acc += out_sz[k];
+        }
+      }
+      const bool direct = ctx->direct_upload.load(std::memory_order_relaxed);
+      size_t staged_to = L.off_region;  // bytes of `stage` that have to be uploaded in one piece
+      std::vector<uint32_t> dma;         // files that are DMA-ed from where they lie
+      for (uint32_t i = 0; i < cnt; ++i) {
+        const uint8_t *src = gst_files[first + i] + GST_HEADER_BYTES;
+        const size_t body = static_cast<size_t>(in_off[4 * i + 3]) + hdrs[i].indices_sz - base[i];
+        bool pinned = false;
+        if (direct) {
+          cudaPointerAttributes attr;
+          pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+          if (!pinned) cudaGetLastError();  // (older drivers report an unregistered pointer as an error)
+        }
+        if (pinned) {
+          dma.push_back(i);
+        } else {
+          memcpy(stage + L.off_region + base[i], src, body);
+          staged_to = L.off_region + base[i] + body;
+        }
+      }
+      // one copy for the offsets region and everything staged behind it (the whole page by default), one per file
+      // that is uploaded directly
+      e = cudaMemcpyAsync(s.d_in, stage, dma.empty() ? staged_to : L.off_region, cudaMemcpyHostToDevice, stream);
+      if (!dma.empty()) {
+        for (uint32_t i = 0; i < cnt && e == cudaSuccess; ++i) {
+          const size_t body = static_cast<size_t>(in_off[4 * i + 3]) + hdrs[i].indices_sz - base[i];
+          const bool is_dma = std::find(dma.begin(), dma.end(), i) != dma.end();
+          const uint8_t *src = is_dma ? gst_files[first + i] + GST_HEADER_BYTES : stage + L.off_region + base[i];
+          e = cudaMemcpyAsync(s.d_in + L.off_region + base[i], src, body, cudaMemcpyHostToDevice, stream);
+        }
+      }
       if (e == cudaSuccess) e = cudaEventRecord(s.h2d_done[j], stream);
       if (e != cudaSuccess) return bail(GST_ERR_CUDA, "upload failed", e);
       // the textures either stay in the caller's device buffer (LoadCompressedDXTs into a PBO,
       // demo/photos_sf.cpp:810-821) or come back to the host (DecompressDXT)
       prc = decode_batch(ctx, hdrs.data(), cnt, stream, s.d_in, s.cap_in, out_on_device ? out + per_image * first : s.d_out,
-                         mode, Taps{}, nullptr, 0, nullptr);
+                         mode, Taps{}, nullptr, 0, nullptr, false, true);
       if (prc) {
         slot_rc[si] = prc;
         slot_err[si] = g_err;
@@ -1240,6 +1301,12 @@ void gst_ans_destroy(gst_ans_decoder *d) {
   if (d->table) cudaFree(d->table);
   if (d->freqs) cudaFree(d->freqs);
   delete d;
+}
+
+int gst_ctx_set_direct_upload(gst_ctx *ctx, int on) {
+  if (!ctx) return fail(GST_ERR_INVALID, "null context");
+  ctx->direct_upload.store(on != 0);
+  return GST_OK;
 }
 
 int gst_status_flags(gst_ctx *ctx, uint32_t *flags, int clear) {

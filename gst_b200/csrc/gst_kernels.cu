@@ -360,12 +360,32 @@ __device__ __forceinline__ ImageStreams image_streams(const BatchParams &p, uint
   // streamer uploads a file as it lies and writes no offset table)
   const uint4 oo = p.inline_off ? make_uint4(p.off8[0], p.off8[1], p.off8[2], p.off8[3]) : __ldg(tbl + b);
   const uint4 io = p.inline_off ? make_uint4(p.off8[4], p.off8[5], p.off8[6], p.off8[7]) : __ldg(tbl + p.n_images + b);
-  s.payload = p.cmp + p.off_region + 2048ull * p.n_images;
+  // standard layout: all frequency blocks, then all payloads.  freq_inline: every image's 2048 bytes of frequency
+  // blocks sit directly in front of its Y stream, as in the .gst file (in_off counts from the end of the offsets
+  // region), so a file is ONE copy
+  s.payload = p.cmp + p.off_region + (p.freq_inline ? 0ull : 2048ull * p.n_images);
   s.out_off[0] = oo.x; s.out_off[1] = oo.y; s.out_off[2] = oo.z; s.out_off[3] = oo.w;
   s.in_off[0] = io.x;  s.in_off[1] = io.y;  s.in_off[2] = io.z;  s.in_off[3] = io.w;
   s.palette_bytes = oo.w - oo.z;
   s.pal_off = oo.z - 7u * p.n_blocks * b - 6u * p.n_blocks;
   return s;
+}
+
+// the 512-byte frequency block of stream `type` of image b (in_off_y = in_off[4b])
+__device__ __forceinline__ const uint8_t *freq_block(const BatchParams &p, uint32_t b, uint32_t type, uint32_t in_off_y) {
+  return p.freq_inline ? p.cmp + p.off_region + in_off_y - 2048u + 512u * type
+                       : p.cmp + p.off_region + 2048ull * b + 512u * type;
+}
+
+// stage 1 for a batch: table 4b + type from the frequency block of that stream, wherever the layout puts it
+__global__ void __launch_bounds__(256) build_tables_batch_kernel(const BatchParams p) {
+  pdl_launch_dependents();
+  __shared__ uint32_t s_sym[kTableSize];
+  __shared__ TableScratch ts;
+  const uint32_t b = blockIdx.x >> 2, type = blockIdx.x & 3;
+  const uint32_t in_off_y = p.inline_off ? p.off8[4] : __ldg(reinterpret_cast<const uint32_t *>(p.cmp) + 4 * (p.n_images + b));
+  build_table_cta(reinterpret_cast<const uint16_t *>(freq_block(p, b, type, in_off_y)), s_sym,
+                  p.tables + static_cast<size_t>(kTableSize) * blockIdx.x, ts);
 }
 
 __device__ __forceinline__ void load_table(uint32_t dst_s, const uint32_t *__restrict__ src,
@@ -595,7 +615,7 @@ __global__ void __launch_bounds__(kRansWarps * 32, RansCfg::kCtasPerSm) rans_str
   if (FT) {
     __shared__ TableScratch ts;
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + (lay.tab - lay.s0));
-    build_table_cta(reinterpret_cast<const uint16_t *>(p.cmp + p.off_region + 2048ull * b + 512u * type), tab, tab, ts);
+    build_table_cta(reinterpret_cast<const uint16_t *>(freq_block(p, b, type, is.in_off[0])), tab, tab, ts);
   } else {
     pdl_wait();  // (the tables come from build_tables_kernel)
     load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
@@ -1381,8 +1401,8 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   const bool small = is_small_call(p.n_images, p.groups_per_plane, max_palette_bytes);
   if (!small) {
     // stage 1: 4 tables per image, straight from the freq region of the compressed buffer
-    e = launch_build_tables(p.cmp + p.off_region, 4 * p.n_images, p.tables, s);
-    if (e != cudaSuccess) return e;
+    build_tables_batch_kernel<<<4 * p.n_images, 256, 0, s>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if ((e = stamp()) != cudaSuccess) return e;
   // stage 2 (+ the group-local part of stage 3): every rANS group of the batch

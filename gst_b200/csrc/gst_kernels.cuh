@@ -66,6 +66,7 @@ struct BatchParams {
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
   uint32_t *status;          // [0]: flags OR-ed in by the kernels (GST_FLAG_*), [1]: a zero word (the palette of an image
                              // whose palette region is unusable)
+  uint32_t freq_inline;      // 1: no frequency region; an image's four frequency blocks precede its Y stream in the payload
   uint32_t inline_off;       // 1: n_images == 1 and the offset table is off8 below, not the first 32 bytes of cmp
   uint32_t off8[8];          // out_off[0..3], in_off[0..3] of that image
   uint32_t kc[8];            // packed constants the wavelet kernel wants in the constant bank (fill_kernel_constants)

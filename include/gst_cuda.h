@@ -144,6 +144,11 @@ int gst_decompress_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, con
 int gst_load_host_batch(gst_ctx *ctx, const uint8_t *const *gst_files, const size_t *lens,
                         uint32_t n, uint32_t page, int mode, void *out_dev, size_t out_cap);
 
+/* Upload policy of the two host batch entry points above.  Off (default): every file is copied into pinned staging
+ * and a page goes up in one DMA.  On: a file that lies in pinned memory is DMA-ed from where it lies (one copy per
+ * file, no host-side packing pass); files in pageable memory are still staged. */
+int gst_ctx_set_direct_upload(gst_ctx *ctx, int on);
+
 /* ---- frame streamer: the headless form of the demo player (demo/demo.cpp:145-243,504-600), which
  * reads frameNNNN.gtc, uploads it, calls LoadCompressedDXT / LoadRGB and blocks on the event
  * before the next frame.  Here `depth` frames are in flight: submit() copies the frame into the

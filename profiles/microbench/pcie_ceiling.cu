@@ -49,6 +49,41 @@ int main() {
       first = false;
     }
   }
+  // one GPU, both directions at once (two streams): what a host -> host decode sees on its link
+  {
+    cudaSetDevice(0);
+    void *d2 = nullptr, *h2 = nullptr;
+    cudaStream_t s2;
+    cudaMalloc(&d2, bytes);
+    cudaHostAlloc(&h2, bytes, cudaHostAllocDefault);
+    cudaStreamCreate(&s2);
+    double best = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+      cudaDeviceSynchronize();
+      const double t0 = now();
+      cudaMemcpyAsync(d[0], h[0], bytes / 4, cudaMemcpyHostToDevice, s[0]);   // the upload is ~ a quarter of the download
+      cudaMemcpyAsync(h2, d2, bytes, cudaMemcpyDeviceToHost, s2);
+      cudaStreamSynchronize(s2);
+      const double t1 = now();
+      cudaStreamSynchronize(s[0]);
+      best = std::min(best, t1 - t0);
+    }
+    printf(",\n  {\"gpus\": 1, \"direction\": \"d2h with a concurrent h2d of a quarter the size on the same GPU\", \"aggregate_gb_s\": %.1f, \"per_gpu_gb_s\": %.1f}",
+           bytes / best / 1e9, bytes / best / 1e9);
+    // many small copies back to back on one stream: 1024 x 640 KB (one .gst file each) against one 640 MB copy
+    const size_t small = 640 << 10;
+    best = 1e30;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaDeviceSynchronize();
+      const double t0 = now();
+      for (int i = 0; i < 1024; ++i)
+        cudaMemcpyAsync(static_cast<char *>(d[0]) + i * small, static_cast<char *>(h[0]) + i * small, small, cudaMemcpyHostToDevice, s[0]);
+      cudaStreamSynchronize(s[0]);
+      best = std::min(best, now() - t0);
+    }
+    printf(",\n  {\"gpus\": 1, \"direction\": \"h2d as 1024 copies of 640 KB on one stream\", \"aggregate_gb_s\": %.1f, \"per_gpu_gb_s\": %.1f}",
+           1024 * small / best / 1e9, 1024 * small / best / 1e9);
+  }
   printf("\n], \"host_memcpy\": [\n");
   // host memcpy: T threads each copying 256 MiB pageable -> pinned (what page packing does)
   const size_t chunk = 256ull << 20;

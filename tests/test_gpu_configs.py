@@ -180,3 +180,29 @@ def test_status_flag_reports_clamped_palette_indices(decoder):
     # block 30 has index 31 * 100 = 3100 > 2047: it carries the last palette entry
     assert out.view("<u4")[1::2][30] == palette.view("<u4")[-1]
     assert out.view("<u4")[1::2][10] == palette.view("<u4")[1100]
+
+
+def test_host_batch_direct_upload_of_pinned_files(decoder):
+    """gst_ctx_set_direct_upload: pinned files are DMA-ed from where they lie, pageable ones staged, in one page."""
+    srcs = [fx.encode_image(512, 512, 10000 + i) for i in range(6)]
+    per = 512 * 512 // 2
+    files = []
+    for i, (g, _) in enumerate(srcs):
+        if i % 2 == 0:
+            pb = decoder.pinned(g.size)
+            pb.array[:] = g
+            files.append(pb)
+        else:
+            files.append(g)
+    d_out = decoder.malloc(per * 6)
+    check(lib().gst_ctx_set_direct_upload(decoder.ctx, 1))
+    try:
+        for page in (6, 4, 1):
+            decoder.memset(d_out, 0xEE)
+            decoder.LoadHostBatch(files, d_out, page=page)
+            got = decoder.download(d_out).reshape(6, per)
+            for i, (_, golden) in enumerate(srcs):
+                assert np.array_equal(got[i], golden), f"page {page}, image {i}"
+    finally:
+        check(lib().gst_ctx_set_direct_upload(decoder.ctx, 0))
+        d_out.free()
