@@ -1,16 +1,19 @@
 // gst_b200 -- sm_100a kernels for the .gst -> DXT1 decode path.
 //
 // Kernel inventory (reference stage it replaces, citations relative to the reference tree):
-//   build_tables_kernel      stage 1  ans/build_table.cl:12-83
+//   build_tables_kernel,     stage 1  ans/build_table.cl:12-83 (flat array of frequency blocks / the blocks of a batch)
+//   build_tables_batch_kernel
 //   rans_streams_kernel      stage 2  ans/ans_decode.cl:25-143 for all four streams of every image,
 //                            one warp per two 32-stream groups.  Plane symbols go to a transposed,
 //                            plane-pair-interleaved scratch, palette symbols to the compact palette,
 //                            and for the index stream stage 3 (codec/decode_indices.cl:6-84, host loop
 //                            codec/decoder.cpp:311-393) is fused behind the rANS warp as a group-local
-//                            suffix sum plus an atomic carry into the later groups
+//                            suffix sum plus a per-group total.  <FT>: stage 1 as well -- the CTA builds its
+//                            table in shared memory (calls too small to fill the machine)
 //   wavelet_assemble_kernel  stage 4 (codec/inverse_wavelet.cl:69-192) and stage 5
 //                            (codec/assemble.cl:64-129): one warp per 32x32 tile, all six planes as
-//                            three packed plane pairs; the wavelet planes never leave shared memory
+//                            three packed plane pairs; the wavelet planes never leave shared memory; the
+//                            cross-group carry of stage 3 is summed here from the group totals
 //   ans_encode_kernel,       the entropy stage of the ENCODER (codec/entropy.cpp:174-265), fixture tooling
 //   ans_encode_gather_kernel
 //   ans_decode_plain_kernel  the standalone `ans_decode` entry (ans/ans_decode.cl:76-95),
@@ -173,7 +176,14 @@ __device__ __forceinline__ void rans_decode_groups(uint32_t tab_s, const uint8_t
   uintptr_t lo[NC];                                  // lo: stream address of that chunk
   uint32_t end[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) end[c] = __ldg(reinterpret_cast<const uint32_t *>(stream) + grp[c]) & ~3u;  // ans/ans_decode.cl:30
+  for (int c = 0; c < NC; ++c) {
+    // ans/ans_decode.cl:30.  The offset table of the stream is caller data too: with inconsistent stream offsets
+    // its address can lie outside the buffer, so it is clamped like everything derived from it
+    uintptr_t a = reinterpret_cast<uintptr_t>(stream) + 4ull * grp[c];
+    a = a < reinterpret_cast<uintptr_t>(buf_lo) ? reinterpret_cast<uintptr_t>(buf_lo) : a;
+    a = a + 4 > hi_ok ? hi_ok - 4 : a;
+    end[c] = __ldg(reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3))) & ~3u;
+  }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     // Clamp so a malformed offset can never leave [buf_lo, buf_hi).
