@@ -592,8 +592,11 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
 // stream (stage 1, ans/build_table.cl) instead of loading the 8 KiB build_tables_kernel left in global memory.  For
 // calls too small to fill the machine this removes a launch and its dependency from the critical path; for large
 // batches every table would be built by up to eight CTAs instead of once, so they keep the separate kernel.
+// (The FT instantiation serves calls that leave most of the machine idle: no occupancy to protect, so it is not held
+// to the 48 registers that 5 CTAs per SM allow -- free of that cap ptxas keeps the table base and the ring
+// addresses in registers instead of recomputing them at every checkpoint, and a lone group finishes 20 % sooner.)
 template <bool TAP, bool FT>
-__global__ void __launch_bounds__(kRansWarps * 32, RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+__global__ void __launch_bounds__(kRansWarps * 32, FT ? 1 : RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   constexpr int NC = RansCfg::kChains;
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();

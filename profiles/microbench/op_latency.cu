@@ -43,6 +43,35 @@ LAT_KERNEL(l_rans_step, {
   v = st;
 })
 
+// two independent chains in one instruction stream (what a decode warp runs), and the same with eight warps per CTA
+#define RANS_STEP(v, off)                                                                         \
+  {                                                                                               \
+    const uint32_t e = tab[(v) & 2047];                                                           \
+    uint32_t st = ((v) >> 11) * (e & 0xFFFu) + (e >> 20) + 0x7000u;                                \
+    const bool need = st < 0x8000u;                                                               \
+    const uint32_t m = __ballot_sync(0xffffffffu, need);                                          \
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(tab) + (off) - 2u * __popc(m & k);      \
+    uint32_t w;                                                                                   \
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(w) : "r"(a)); \
+    if (need) st = (st << 16) | w;                                                                \
+    (v) = st;                                                                                     \
+  }
+__global__ void l_rans_step2(uint32_t *out, uint32_t seed, long long *cyc) {
+  __shared__ uint32_t tab[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) tab[i] = (i * 2654435761u + seed) & 2047;
+  __syncthreads();
+  uint32_t v = (threadIdx.x * 37 + seed) & 2047, v2 = (threadIdx.x * 41 + seed + 7) & 2047, k = seed | 1;
+  long long t0 = clock64();
+#pragma unroll 8
+  for (int i = 0; i < REP; ++i) {
+    RANS_STEP(v, 4096u)
+    RANS_STEP(v2, 6144u)
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) *cyc = t1 - t0;
+  out[threadIdx.x] = v + v2 + k + tab[0];
+}
+
 typedef void (*kern_t)(uint32_t *, uint32_t, long long *);
 int main() {
   uint32_t *out; long long *cyc, h;
@@ -58,6 +87,12 @@ int main() {
     e.k<<<1, 32>>>(out, 1, cyc); cudaDeviceSynchronize();
     cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
     printf("%-32s %8.1f\n", e.name, double(h) / REP);
+  }
+  for (int threads : {32, 128, 256, 512, 1024}) {
+    l_rans_step2<<<1, threads>>>(out, 1, cyc); cudaDeviceSynchronize();
+    l_rans_step2<<<1, threads>>>(out, 1, cyc); cudaDeviceSynchronize();
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("rANS step, 2 chains, %4d threads   %8.1f\n", threads, double(h) / REP);
   }
   return 0;
 }

@@ -8,7 +8,7 @@ for v in gst_b200/lib/var/*.so; do
     GST_LIB=$PWD/$v python bench.py --no-e2e --no-cpu-baseline --steps 20 "$@" 2>gpurun_out/ab_$(basename $v .so).err | tail -1 | python -c "
 import sys,json
 try:
-    d=json.loads(sys.stdin.read()); print('$(basename $v .so)', round(d['value'],1), 'ms', round(d['ms_per_step'],4), {k: round(v,4) for k,v in d['roofline']['kernel_ms_all'].items()})
+    d=json.loads(sys.stdin.read()); print('$(basename $v .so)', round(d['value'],1), 'ms', round(d['ms_per_step'],4), {k: round(v['ms'],4) for k,v in d['roofline']['kernels'].items()})
 except Exception as e: print('$(basename $v .so)', 'FAILED', e)"
   done
 done
