@@ -592,11 +592,11 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
 // stream (stage 1, ans/build_table.cl) instead of loading the 8 KiB build_tables_kernel left in global memory.  For
 // calls too small to fill the machine this removes a launch and its dependency from the critical path; for large
 // batches every table would be built by up to eight CTAs instead of once, so they keep the separate kernel.
-// (The FT instantiation serves calls that leave most of the machine idle: no occupancy to protect, so it is not held
-// to the 48 registers that 5 CTAs per SM allow -- free of that cap ptxas keeps the table base and the ring
-// addresses in registers instead of recomputing them at every checkpoint, and a lone group finishes 20 % sooner.)
-template <bool TAP, bool FT>
-__global__ void __launch_bounds__(kRansWarps * 32, FT ? 1 : RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+// LONE: the grid fits the machine at three CTAs per SM, so there is no occupancy to protect and the kernel is not held
+// to the 48 registers that 5 CTAs per SM allow -- free of that cap ptxas keeps the table base and the ring addresses
+// in registers instead of recomputing them at every checkpoint (72 registers), and a lone group finishes 20 % sooner.
+template <bool TAP, bool FT, bool LONE>
+__global__ void __launch_bounds__(kRansWarps * 32, LONE ? 3 : RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
   constexpr int NC = RansCfg::kChains;
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
@@ -1369,8 +1369,9 @@ static cudaError_t ensure_attrs() {
                     wavelet_assemble_kernel<0, true, false>, wavelet_assemble_kernel<1, true, false>}) {
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaSmem)) != cudaSuccess) return e;
     }
-    for (auto *k : {rans_streams_kernel<false, false>, rans_streams_kernel<true, false>, rans_streams_kernel<false, true>,
-                    rans_streams_kernel<true, true>}) {
+    for (auto *k : {rans_streams_kernel<false, false, false>, rans_streams_kernel<true, false, false>,
+                    rans_streams_kernel<false, true, false>, rans_streams_kernel<true, true, false>,
+                    rans_streams_kernel<false, true, true>, rans_streams_kernel<true, true, true>}) {
       if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RansCfg::kSmem)) != cudaSuccess) return e;
     }
     return cudaFuncSetAttribute(ans_decode_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem);
@@ -1428,12 +1429,15 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   // the stage taps (parity tests only) are a separate instantiation: the production kernels carry none of that code
   const bool taps = p.tap_symbols || p.tap_planes || p.tap_indices;
   const dim3 rans_grid(p.n_images * sg.per_image()), rans_block(kRansWarps * 32);
-  if (small) {
-    e = taps ? launch_kernel(rans_streams_kernel<true, true>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg)
-             : launch_kernel(rans_streams_kernel<false, true>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg);
+  if (small && rans_grid.x <= 3u * 148u) {
+    e = taps ? launch_kernel(rans_streams_kernel<true, true, true>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg)
+             : launch_kernel(rans_streams_kernel<false, true, true>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg);
+  } else if (small) {
+    e = taps ? launch_kernel(rans_streams_kernel<true, true, false>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg)
+             : launch_kernel(rans_streams_kernel<false, true, false>, rans_grid, rans_block, RansCfg::kSmem, s, false, p, sg);
   } else {
-    e = taps ? launch_kernel(rans_streams_kernel<true, false>, rans_grid, rans_block, RansCfg::kSmem, s, pdl, p, sg)
-             : launch_kernel(rans_streams_kernel<false, false>, rans_grid, rans_block, RansCfg::kSmem, s, pdl, p, sg);
+    e = taps ? launch_kernel(rans_streams_kernel<true, false, false>, rans_grid, rans_block, RansCfg::kSmem, s, pdl, p, sg)
+             : launch_kernel(rans_streams_kernel<false, false, false>, rans_grid, rans_block, RansCfg::kSmem, s, pdl, p, sg);
   }
   if (e != cudaSuccess) return e;
   if ((e = stamp()) != cudaSuccess) return e;
