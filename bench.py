@@ -60,8 +60,10 @@ def parse_args():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="strong",
                     help="strong (default): the configured batch is the job, image / frame i goes to rank i mod N; "
                          "weak: every GPU decodes the whole configured batch")
-    ap.add_argument("--direct-upload", action="store_true",
-                    help="e2e legs: DMA every pinned .gst file from where it lies instead of packing pages (gst_ctx_set_direct_upload)")
+    ap.add_argument("--upload", choices=["auto", "staged", "direct"], default="auto",
+                    help="e2e legs: pack pages into pinned staging (staged) or DMA every pinned .gst file from where it "
+                         "lies (direct, gst_ctx_set_direct_upload).  auto: staged up to 2 GPUs (the link is the limit and "
+                         "one big copy beats 1024 small ones), direct from 4 GPUs on (the host memory system is)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample")
@@ -239,7 +241,8 @@ def main():
     from gst_b200.shard import reduce_job, shard_indices
 
     dec = gst_b200.Decoder(local_rank)
-    if args.direct_upload:
+    direct = args.upload == "direct" or (args.upload == "auto" and world >= 4)
+    if direct:
         check(lib().gst_ctx_set_direct_upload(dec.ctx, 1))
     distinct = min(args.distinct, images_total)
     files, goldens = load_streams(args.config, width, height, distinct, rank, world)
@@ -415,7 +418,7 @@ def main():
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
                "api": "gst_streamer_play (per frame: direct upload, decode, read-back on the slot's stream)"
-                      if streamer is not None else "gst_decompress_host_batch",
+                      if streamer is not None else "gst_decompress_host_batch, " + ("direct" if direct else "staged") + " upload",
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
         if streamer is not None:
             e2e["frames_per_s"] = images_total * e2e_steps / dt
