@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--images", type=int, default=0, help="override images per GPU")
     ap.add_argument("--distinct", type=int, default=32, help="distinct encoded images tiled to the batch")
     ap.add_argument("--page", type=int, default=32, help="images per page on the e2e path")
-    ap.add_argument("--depth", type=int, default=4, help="frames in flight of the configs[4] frame streamer")
+    ap.add_argument("--depth", type=int, default=4, help="groups of frames in flight of the configs[4] frame streamer")
+    ap.add_argument("--group", type=int, default=0, help="frames per decode call of gst_streamer_play (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="strong",
                     help="strong (default): the configured batch is the job, image / frame i goes to rank i mod N; "
@@ -400,7 +401,7 @@ def main():
             # configs[4]: the demo player loop (demo/demo.cpp:145-243) with `depth` frames in flight: every frame is
             # uploaded from where it lies, decoded and copied back to the host on its slot's stream; a frame is
             # waited for `depth - 1` submissions after its own
-            streamer.play(ptrs, lens, images, host_out=pin_out.ptr, direct=True)
+            streamer.play(ptrs, lens, images, host_out=pin_out.ptr, direct=True, group=args.group)
 
         pin_out.array[:] = 0xEE
         e2e_step()  # warm-up: grows the staging buffers
@@ -417,7 +418,7 @@ def main():
                "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(d2h_job),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
-               "api": "gst_streamer_play (per frame: direct upload, decode, read-back on the slot's stream)"
+               "api": "gst_streamer_play (direct upload per frame; decode and read-back per group of frames on the slot's stream)"
                       if streamer is not None else "gst_decompress_host_batch, " + ("direct" if direct else "staged") + " upload",
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
         if streamer is not None:

@@ -119,7 +119,7 @@ struct gst_streamer {
   uint64_t next_ticket = 0;
   struct Slot {
     uint8_t *pinned = nullptr, *d_in = nullptr, *d_out = nullptr;
-    size_t cap_in = 0;
+    size_t cap_in = 0, cap_out = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     uint64_t ticket = UINT64_MAX;  // frame currently (or last) in the slot
@@ -996,6 +996,7 @@ int gst_streamer_create(gst_ctx *ctx, uint32_t width, uint32_t height, uint32_t 
     cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_out), st->frame_bytes);
+    if (e == cudaSuccess) s.cap_out = st->frame_bytes;
     if (e != cudaSuccess) {
       gst_streamer_destroy(st);
       return fail(GST_ERR_CUDA, "streamer allocation failed: %s", cudaGetErrorString(e));
@@ -1078,25 +1079,112 @@ int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, voi
   return streamer_submit(st, gst, len, out_dev, out_host, ticket, (flags & GST_SUBMIT_DIRECT) != 0);
 }
 
+namespace {
+// k consecutive frames as ONE LoadCompressedDXTs-style call on slot `slot_no` (gst_streamer_play): k uploads (straight from
+// the caller's buffers when `direct`), the offsets table, two kernel launches, ONE read-back of the k frames.
+int streamer_submit_group(gst_streamer *st, uint32_t slot_no, const uint8_t *const *frames, const size_t *lens, uint32_t k,
+                          uint8_t *out_dev, uint8_t *out_host, bool direct) {
+  gst_streamer::Slot &s = st->slots[slot_no];
+  std::vector<gst_header> hdrs(k);
+  size_t body_total = 0;
+  for (uint32_t i = 0; i < k; ++i) {
+    int rc = gst_parse_header(frames[i], lens[i], &hdrs[i]);
+    if (rc) return rc;
+    if (hdrs[i].width != st->width || hdrs[i].height != st->height)
+      return fail(GST_ERR_INVALID, "frame is %ux%u, the streamer was created for %ux%u", hdrs[i].width, hdrs[i].height,
+                  st->width, st->height);
+    body_total += lens[i] - GST_HEADER_BYTES;
+  }
+  BatchLayout L;
+  int rc = layout_batch(hdrs.data(), k, &L);
+  if (rc) return rc;
+  // the slot's previous work must be done: its staging and buffers are reused
+  if (s.ticket != UINT64_MAX) GST_CUDA_TRY(cudaEventSynchronize(s.done));
+  const size_t need = L.off_region + body_total;
+  if (need > s.cap_in) {
+    if (s.pinned) cudaFreeHost(s.pinned);
+    if (s.d_in) cudaFree(s.d_in);
+    s.pinned = s.d_in = nullptr;
+    s.cap_in = align_up(need + need / 2, 4096);
+    GST_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s.pinned), s.cap_in, cudaHostAllocDefault));
+    GST_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s.d_in), s.cap_in));
+  }
+  if (!out_dev && st->frame_bytes * k > s.cap_out) {
+    if (s.d_out) cudaFree(s.d_out);
+    s.d_out = nullptr;
+    s.cap_out = st->frame_bytes * k;
+    GST_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s.d_out), s.cap_out));
+  }
+  // page layout of the host batch loader: [offsets][frame 0 minus its header][frame 1 ...], frequency blocks inline
+  uint32_t *out_off = reinterpret_cast<uint32_t *>(s.pinned), *in_off = out_off + 4 * k;
+  memset(s.pinned, 0, L.off_region);
+  uint32_t in_acc = 0, out_acc = 0;
+  std::vector<uint32_t> base(k);
+  for (uint32_t i = 0; i < k; ++i) {
+    const gst_header &h = hdrs[i];
+    const uint32_t in_sz[4] = {h.y_cmp_sz, h.chroma_cmp_sz, h.palette_sz, h.indices_sz};
+    const uint32_t out_sz[4] = {2 * L.n_blocks, 4 * L.n_blocks, h.palette_bytes, L.n_blocks};
+    base[i] = in_acc;
+    in_acc += 2048;
+    for (int q = 0; q < 4; ++q) {
+      in_off[4 * i + q] = in_acc;
+      out_off[4 * i + q] = out_acc;
+      in_acc += in_sz[q];
+      out_acc += out_sz[q];
+    }
+  }
+  if (direct) {
+    GST_CUDA_TRY(cudaMemcpyAsync(s.d_in, s.pinned, L.off_region, cudaMemcpyHostToDevice, s.stream));
+    for (uint32_t i = 0; i < k; ++i)
+      GST_CUDA_TRY(cudaMemcpyAsync(s.d_in + L.off_region + base[i], frames[i] + GST_HEADER_BYTES, lens[i] - GST_HEADER_BYTES,
+                                   cudaMemcpyHostToDevice, s.stream));
+  } else {
+    for (uint32_t i = 0; i < k; ++i) memcpy(s.pinned + L.off_region + base[i], frames[i] + GST_HEADER_BYTES, lens[i] - GST_HEADER_BYTES);
+    GST_CUDA_TRY(cudaMemcpyAsync(s.d_in, s.pinned, need, cudaMemcpyHostToDevice, s.stream));
+  }
+  uint8_t *dst = out_dev ? out_dev : s.d_out;
+  rc = decode_batch(st->ctx, hdrs.data(), k, s.stream, s.d_in, s.cap_in, dst, st->mode, Taps{}, nullptr, 0, nullptr, false, true);
+  if (rc) return rc;
+  if (out_host) GST_CUDA_TRY(cudaMemcpyAsync(out_host, dst, st->frame_bytes * k, cudaMemcpyDeviceToHost, s.stream));
+  GST_CUDA_TRY(cudaEventRecord(s.done, s.stream));
+  s.ticket = 0;  // (in use; frames of a group have no tickets of their own)
+  s.frame_dev = dst;
+  return GST_OK;
+}
+}  // namespace
+
 // The demo's main loop (demo/demo.cpp:504-600: for every frame load the file, decode it, hand it on) over a sequence
-// that is already in host memory, `depth` frames in flight.
+// that is already in host memory.  Frames are taken `group` at a time (GST_PLAY_GROUP in flags, default 4): one
+// LoadCompressedDXTs-style call and one read-back per group instead of per frame, `depth` groups in flight -- per
+// frame that leaves one upload and a quarter of everything else, which is what lets one host thread keep the PCIe
+// link busy.
 int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size_t *lens, uint32_t n, void *out_dev,
                       void *out_host, uint32_t flags) {
   if (!st || !frames || !lens) return fail(GST_ERR_INVALID, "null argument");
-  const uint64_t first = st->next_ticket;
-  const uint32_t lag = st->depth - 1;
-  for (uint32_t f = 0; f < n; ++f) {
+  if (flags & ~(GST_SUBMIT_DIRECT | 0xFF00u)) return fail(GST_ERR_INVALID, "unknown play flags 0x%x", flags);
+  uint32_t group = (flags >> 8) & 0xFFu;
+  if (group == 0) group = 4;
+  DeviceGuard guard(st->ctx->device);
+  // frames submitted one by one before this call must have drained: their slots are reused
+  for (auto &s : st->slots)
+    if (s.ticket != UINT64_MAX) GST_CUDA_TRY(cudaEventSynchronize(s.done));
+  int rc = GST_OK;
+  uint32_t g = 0;
+  for (uint32_t f = 0; f < n && rc == GST_OK; f += group, ++g) {
+    const uint32_t k = std::min(group, n - f);
     uint8_t *od = out_dev ? static_cast<uint8_t *>(out_dev) + static_cast<size_t>(f) * st->frame_bytes : nullptr;
     uint8_t *oh = out_host ? static_cast<uint8_t *>(out_host) + static_cast<size_t>(f) * st->frame_bytes : nullptr;
-    int rc = gst_streamer_submit_ex(st, frames[f], lens[f], od, oh, flags, nullptr);
-    if (rc) return rc;
-    if (f >= lag && (rc = gst_streamer_wait(st, first + f - lag, nullptr))) return rc;
+    rc = streamer_submit_group(st, g % st->depth, frames + f, lens + f, k, od, oh, (flags & GST_SUBMIT_DIRECT) != 0);
   }
-  for (uint32_t f = n > lag ? n - lag : 0; f < n; ++f) {
-    int rc = gst_streamer_wait(st, first + f, nullptr);
-    if (rc) return rc;
+  for (auto &s : st->slots) {
+    if (s.ticket != UINT64_MAX) {
+      cudaError_t e = cudaEventSynchronize(s.done);
+      if (e != cudaSuccess && rc == GST_OK) rc = fail(GST_ERR_CUDA, "frame decode failed: %s", cudaGetErrorString(e));
+    }
+    s.ticket = UINT64_MAX;
   }
-  return GST_OK;
+  st->next_ticket += n;
+  return rc;
 }
 
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev) {

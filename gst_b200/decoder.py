@@ -424,9 +424,11 @@ class FrameStreamer:
                                                1 if direct else 0, C.byref(t)))
         return t.value
 
-    def play(self, frame_ptrs, frame_lens, n, host_out=None, dev_out=None, direct=False):
-        """gst_streamer_play: the whole frame loop in one call (ctypes arrays of addresses and sizes)."""
-        check(lib().gst_streamer_play(self.handle, frame_ptrs, frame_lens, n, dev_out, host_out, 1 if direct else 0))
+    def play(self, frame_ptrs, frame_lens, n, host_out=None, dev_out=None, direct=False, group=0):
+        """gst_streamer_play: the whole frame loop in one call (ctypes arrays of addresses and sizes); `group`
+        frames per decode call (0 = the library's default, 4)."""
+        flags = (1 if direct else 0) | ((int(group) & 0xFF) << 8)
+        check(lib().gst_streamer_play(self.handle, frame_ptrs, frame_lens, n, dev_out, host_out, flags))
 
     def wait(self, ticket):
         """Blocks until the frame is decoded; returns its device address."""

@@ -171,9 +171,11 @@ int gst_streamer_submit(gst_streamer *st, const uint8_t *gst, size_t len, void *
 int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, void *out_dev, void *out_host,
                            uint32_t flags, uint64_t *ticket);
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev);
-/* The player's main loop (demo/demo.cpp:504-600) over n frames already in host memory: frame f is submitted with
- * gst_streamer_submit_ex (out_dev / out_host, when not NULL, advance by one decoded frame per f) and waited for
- * depth - 1 submissions later; returns when every frame is done. */
+/* The player's main loop (demo/demo.cpp:504-600) over n frames already in host memory.  out_dev / out_host, when not
+ * NULL, receive frame f at f decoded frames from their start.  Frames are decoded GST_PLAY_GROUP(k) at a time (default
+ * 4): one LoadCompressedDXTs-style call and one read-back per group, `depth` groups in flight; GST_SUBMIT_DIRECT as
+ * for gst_streamer_submit_ex.  Returns when every frame is done; frames played this way have no tickets. */
+#define GST_PLAY_GROUP(k) (((uint32_t)(k) & 0xFFu) << 8)
 int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size_t *lens, uint32_t n,
                       void *out_dev, void *out_host, uint32_t flags);
 void gst_streamer_destroy(gst_streamer *st);

@@ -206,3 +206,36 @@ def test_host_batch_direct_upload_of_pinned_files(decoder):
     finally:
         check(lib().gst_ctx_set_direct_upload(decoder.ctx, 0))
         d_out.free()
+
+
+@pytest.mark.parametrize("group,direct", [(1, True), (3, False), (4, True)])
+def test_streamer_play_groups(decoder, group, direct):
+    """gst_streamer_play with `group` frames per decode call: a ragged last group, staged and direct uploads, the
+    frames left in a caller's device buffer and in host memory."""
+    srcs = [fx.encode_image(512, 512, 10000 + i) for i in range(5)]
+    per = 512 * 512 // 2
+    n = 11
+    pins = []
+    for g, _ in srcs:
+        pb = decoder.pinned(g.size)
+        pb.array[:] = g
+        pins.append(pb)
+    ptrs = (C.c_void_p * n)(*[pins[f % 5].ptr for f in range(n)])
+    lens = (C.c_size_t * n)(*[pins[f % 5].nbytes for f in range(n)])
+    host = decoder.pinned(per * n)
+    host.array[:] = 0
+    d_out = decoder.malloc(per * n)
+    decoder.memset(d_out, 0xEE)
+    st = gst_b200.FrameStreamer(decoder, 512, 512, depth=2)
+    try:
+        st.play(ptrs, lens, n, host_out=host.ptr, dev_out=d_out.ptr, direct=direct, group=group)
+        # single submissions still work on the same streamer afterwards
+        t = st.submit(srcs[0][0])
+        assert np.array_equal(st.read(t), srcs[0][1])
+    finally:
+        st.close()
+    dev = decoder.download(d_out)
+    for f in range(n):
+        assert np.array_equal(host.array[f * per:(f + 1) * per], srcs[f % 5][1]), f"host frame {f}"
+        assert np.array_equal(dev[f * per:(f + 1) * per], srcs[f % 5][1]), f"device frame {f}"
+    d_out.free()
