@@ -1012,6 +1012,14 @@ void gst_streamer_destroy(gst_streamer *st) {
   for (auto &s : st->slots) {
     if (s.stream) {
       cudaStreamSynchronize(s.stream);
+      {  // the scratch the context kept for this stream goes with it
+        std::lock_guard<std::mutex> lock(st->ctx->scratch_mutex);
+        auto it = st->ctx->stream_scratch.find(s.stream);
+        if (it != st->ctx->stream_scratch.end()) {
+          if (it->second && it->second->ptr) cudaFree(it->second->ptr);
+          st->ctx->stream_scratch.erase(it);
+        }
+      }
       cudaStreamDestroy(s.stream);
     }
     if (s.done) cudaEventDestroy(s.done);
