@@ -398,10 +398,10 @@ def main():
             if streamer is None:
                 check(lib().gst_decompress_host_batch(dec.ctx, ptrs, lens, images, args.page, 0, pin_out.ptr, pin_out.nbytes))
                 return
-            # configs[4]: the demo player loop (demo/demo.cpp:145-243) with `depth` frames in flight: every frame is
-            # uploaded from where it lies, decoded and copied back to the host on its slot's stream; a frame is
-            # waited for `depth - 1` submissions after its own
-            streamer.play(ptrs, lens, images, host_out=pin_out.ptr, direct=True, group=args.group)
+            # configs[4]: the demo player loop (demo/demo.cpp:145-243, 504-600) with `depth` groups of frames in flight:
+            # every frame is copied into its slot's pinned staging, a group goes up in one DMA, is decoded in one call
+            # and copied back to the host on the slot's stream
+            streamer.play(ptrs, lens, images, host_out=pin_out.ptr, direct=False, group=args.group)
 
         pin_out.array[:] = 0xEE
         e2e_step()  # warm-up: grows the staging buffers
@@ -418,7 +418,7 @@ def main():
                "h2d_bytes_per_step": int(h2d_job), "d2h_bytes_per_step": int(d2h_job),
                "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "page_images": args.page,
                "compressed_gb_s": cmp_job * e2e_steps / dt / 1e9,
-               "api": "gst_streamer_play (direct upload per frame; decode and read-back per group of frames on the slot's stream)"
+               "api": "gst_streamer_play (staged upload, decode and read-back per group of frames on the slot's stream)"
                       if streamer is not None else "gst_decompress_host_batch, " + ("direct" if direct else "staged") + " upload",
                "timing": "host wall clock around blocking calls (copies + kernels inside), max over ranks"}
         if streamer is not None:

@@ -1162,16 +1162,19 @@ int streamer_submit_group(gst_streamer *st, uint32_t slot_no, const uint8_t *con
 }  // namespace
 
 // The demo's main loop (demo/demo.cpp:504-600: for every frame load the file, decode it, hand it on) over a sequence
-// that is already in host memory.  Frames are taken `group` at a time (GST_PLAY_GROUP in flags, default 4): one
+// that is already in host memory.  Frames are taken `group` at a time (GST_PLAY_GROUP in flags, default 8): one
 // LoadCompressedDXTs-style call and one read-back per group instead of per frame, `depth` groups in flight -- per
-// frame that leaves one upload and a quarter of everything else, which is what lets one host thread keep the PCIe
-// link busy.
+// frame that leaves one host copy (or one upload) and an eighth of everything else, which is what lets one host
+// thread keep the PCIe link busy: 600 frames of 1920x1024 with read-back, frames per second on one B200 --
+// 30 k one by one, 47 k in groups of 4, 50 k in groups of 16 with staged uploads (the read-back floor is 58 k);
+// with GST_SUBMIT_DIRECT 39 k whatever the group (many small uploads slow the read-back beside them down), so
+// direct upload pays only when the frames are not read back (89-94 k against 61 k one by one).
 int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size_t *lens, uint32_t n, void *out_dev,
                       void *out_host, uint32_t flags) {
   if (!st || !frames || !lens) return fail(GST_ERR_INVALID, "null argument");
   if (flags & ~(GST_SUBMIT_DIRECT | 0xFF00u)) return fail(GST_ERR_INVALID, "unknown play flags 0x%x", flags);
   uint32_t group = (flags >> 8) & 0xFFu;
-  if (group == 0) group = 4;
+  if (group == 0) group = 8;
   DeviceGuard guard(st->ctx->device);
   // frames submitted one by one before this call must have drained: their slots are reused
   for (auto &s : st->slots)

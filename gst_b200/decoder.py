@@ -426,7 +426,7 @@ class FrameStreamer:
 
     def play(self, frame_ptrs, frame_lens, n, host_out=None, dev_out=None, direct=False, group=0):
         """gst_streamer_play: the whole frame loop in one call (ctypes arrays of addresses and sizes); `group`
-        frames per decode call (0 = the library's default, 4)."""
+        frames per decode call (0 = the library's default, 8)."""
         flags = (1 if direct else 0) | ((int(group) & 0xFF) << 8)
         check(lib().gst_streamer_play(self.handle, frame_ptrs, frame_lens, n, dev_out, host_out, flags))
 

@@ -173,8 +173,9 @@ int gst_streamer_submit_ex(gst_streamer *st, const uint8_t *gst, size_t len, voi
 int gst_streamer_wait(gst_streamer *st, uint64_t ticket, void **frame_dev);
 /* The player's main loop (demo/demo.cpp:504-600) over n frames already in host memory.  out_dev / out_host, when not
  * NULL, receive frame f at f decoded frames from their start.  Frames are decoded GST_PLAY_GROUP(k) at a time (default
- * 4): one LoadCompressedDXTs-style call and one read-back per group, `depth` groups in flight; GST_SUBMIT_DIRECT as
- * for gst_streamer_submit_ex.  Returns when every frame is done; frames played this way have no tickets. */
+ * 8): one LoadCompressedDXTs-style call and one read-back per group, `depth` groups in flight; GST_SUBMIT_DIRECT as
+ * for gst_streamer_submit_ex (it pays when the frames stay on the device; with a read-back the staged upload is
+ * faster).  Returns when every frame is done; frames played this way have no tickets. */
 #define GST_PLAY_GROUP(k) (((uint32_t)(k) & 0xFFu) << 8)
 int gst_streamer_play(gst_streamer *st, const uint8_t *const *frames, const size_t *lens, uint32_t n,
                       void *out_dev, void *out_host, uint32_t flags);
