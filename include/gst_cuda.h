@@ -247,7 +247,7 @@ int gst_build_tables(gst_ctx *ctx, void *stream, const void *freqs_dev, uint32_t
 /* number of kernel launches one gst_load_*_batch call enqueues, in launch order:
  * build_tables, rans_streams (all four streams + the group-local index scan), wavelet_assemble.
  * gst_launches_for_batch: the number for these headers -- 2 when the call is too small to fill the GPU (at most
- * 4096 rANS groups): the consuming CTAs build their tables themselves. */
+ * 16384 rANS groups): the consuming CTAs build their tables themselves. */
 int gst_launches_per_batch(void);
 int gst_launches_for_batch(const gst_header *hdrs, uint32_t n);
 

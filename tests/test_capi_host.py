@@ -152,14 +152,15 @@ def test_normalize_frequencies_matches_reference(ref_lib):
 
 
 def test_launch_count_and_stream_size_checks_are_host_logic():
-    """gst_launches_for_batch (2 launches for calls of at most 4096 rANS groups, else 3) and the per-stream minimum
+    """gst_launches_for_batch (2 launches for calls of at most 16384 rANS groups, else 3) and the per-stream minimum
     size every entry point now checks need no device."""
     import gst_b200
     from gst_b200.capi import gst_header, lib
     h = gst_b200.parse_header(fx.golden_test1()[0]).to_c()
     assert lib().gst_launches_for_batch((gst_header * 1)(h), 1) == 2
     assert lib().gst_launches_for_batch((gst_header * 128)(*[h] * 128), 128) == 2       # 128 x 15 groups
-    assert lib().gst_launches_for_batch((gst_header * 512)(*[h] * 512), 512) == 3
+    assert lib().gst_launches_for_batch((gst_header * 512)(*[h] * 512), 512) == 2       # 7 680 groups
+    assert lib().gst_launches_for_batch((gst_header * 2048)(*[h] * 2048), 2048) == 3
     bad = gst_header(width=512, height=512, palette_bytes=8192, y_cmp_sz=64, chroma_cmp_sz=64, palette_sz=64, indices_sz=64)
     assert lib().gst_launches_for_batch((gst_header * 1)(bad), 1) == 0                  # 4 groups cannot fit in 64 bytes
     assert lib().gst_packed_size((gst_header * 1)(bad), 1) == 0

@@ -154,9 +154,10 @@ def test_launch_count_small_and_large_calls(decoder):
     small = gst_b200.parse_header(fx.golden_test1()[0])
     big = gst_b200.parse_header(fx.encode_image(2048, 2048, 30000)[0])
     one = (gst_b200.capi.gst_header * 1)(small.to_c())
-    many = (gst_b200.capi.gst_header * 32)(*[big.to_c()] * 32)
+    many = (gst_b200.capi.gst_header * 128)(*[big.to_c()] * 128)
     assert lib().gst_launches_for_batch(one, 1) == 2      # tables built by the consuming CTAs
-    assert lib().gst_launches_for_batch(many, 32) == 3
+    assert lib().gst_launches_for_batch(many, 32) == 2    # 32 x 2048^2: still under 16 384 groups
+    assert lib().gst_launches_for_batch(many, 128) == 3
     assert lib().gst_launches_per_batch() == 3
 
 
