@@ -63,8 +63,8 @@ def parse_args():
                          "weak: every GPU decodes the whole configured batch")
     ap.add_argument("--upload", choices=["auto", "staged", "direct"], default="auto",
                     help="e2e legs: pack pages into pinned staging (staged) or DMA every pinned .gst file from where it "
-                         "lies (direct, gst_ctx_set_direct_upload).  auto: staged up to 2 GPUs (the link is the limit and "
-                         "one big copy beats 1024 small ones), direct from 4 GPUs on (the host memory system is)")
+                         "lies (direct, gst_ctx_set_direct_upload).  auto: staged on one GPU (the link is the limit and "
+                         "one big copy beats 1024 small ones), direct from 2 GPUs on (the host memory system is)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample")
@@ -242,7 +242,7 @@ def main():
     from gst_b200.shard import reduce_job, shard_indices
 
     dec = gst_b200.Decoder(local_rank)
-    direct = args.upload == "direct" or (args.upload == "auto" and world >= 4)
+    direct = args.upload == "direct" or (args.upload == "auto" and world >= 2)
     if direct:
         check(lib().gst_ctx_set_direct_upload(dec.ctx, 1))
     distinct = min(args.distinct, images_total)
