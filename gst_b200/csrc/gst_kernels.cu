@@ -460,11 +460,7 @@ struct RansCfg {
   static constexpr int kChains = 2;
   static constexpr int kGroupsPerCta = kRansWarps * kChains;
   static constexpr int kSmem = kGroupsPerCta * kRingSlot + kTableSize * 4 + kRingSlot;  // + alignment slack
-#ifdef GST_RANS_CTAS
-  static constexpr int kCtasPerSm = GST_RANS_CTAS;
-#else
   static constexpr int kCtasPerSm = 5;
-#endif
 };
 
 // CTAs of one image: [Y][chroma][palette][index]
@@ -929,11 +925,7 @@ __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t 
 //             stores; palette index = run_end - S.  The index / palette loads of the next slab
 //             are in flight while a slab is assembled, those of slab 0 during the wavelet.
 constexpr int kWaWarps = 2;
-#ifdef GST_WA_PAD
-constexpr int kWaSmem = kWaWarps * kWarpWork + GST_WA_PAD;  // occupancy experiment
-#else
 constexpr int kWaSmem = kWaWarps * kWarpWork;  // 24576
-#endif
 
 // IDX16: the index suffix sums are u16 (every palette of the batch has <= 65536 entries), else u32.
 template <int RGB, bool TAP, bool IDX16>
