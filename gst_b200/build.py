@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgst_cuda.so")
 SOURCES = ["gst_kernels.cu", "gst_capi.cu"]
 DEPS = SOURCES + ["gst_kernels.cuh", os.path.join("..", "..", "include", "gst_cuda.h")]
-# GST_NVCC_EXTRA: extra nvcc flags (e.g. -DSOME_VARIANT) for A/B builds, see scripts/ab_bench.sh
+# GST_NVCC_EXTRA: extra nvcc flags (e.g. -DSOME_VARIANT) for A/B builds, see scripts/build_var.sh and scripts/ab.sh
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared", "-x", "cu",
