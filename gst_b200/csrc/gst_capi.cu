@@ -72,6 +72,17 @@ struct gst_ctx {
                    // regrow the buffer in between
     uint8_t *ptr = nullptr;
     size_t cap = 0;
+    // hand-over counters of the calls on this stream (BatchParams::img_done / tiles_done): 2 x sync_cap words, zero
+    // whenever no call is running (the kernels leave them so); also used by calls that take their scratch from the arena
+    uint32_t *sync = nullptr;
+    size_t sync_cap = 0;
+    void release() {
+      if (ptr) cudaFree(ptr);
+      if (sync) cudaFree(sync);
+      ptr = nullptr;
+      sync = nullptr;
+      cap = sync_cap = 0;
+    }
   };
   std::mutex scratch_mutex;
   std::unordered_map<cudaStream_t, std::unique_ptr<StreamScratch>> stream_scratch;
@@ -256,17 +267,18 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
       from_arena = true;
     }
   }
-  std::unique_lock<std::mutex> scratch_lock;
+  // the stream's record is held from here to the last launch of the call: a concurrent call on the same stream must
+  // neither regrow the buffers in between nor interleave its kernels with ours (the hand-over counters are per stream)
+  gst_ctx::StreamScratch *ssp = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ctx->scratch_mutex);
+    std::unique_ptr<gst_ctx::StreamScratch> &slot = ctx->stream_scratch[stream];
+    if (!slot) slot.reset(new gst_ctx::StreamScratch);
+    ssp = slot.get();
+  }
+  std::unique_lock<std::mutex> scratch_lock(ssp->m);
+  gst_ctx::StreamScratch &ss = *ssp;
   if (!from_arena) {
-    gst_ctx::StreamScratch *ssp = nullptr;
-    {
-      std::lock_guard<std::mutex> lock(ctx->scratch_mutex);
-      std::unique_ptr<gst_ctx::StreamScratch> &slot = ctx->stream_scratch[stream];
-      if (!slot) slot.reset(new gst_ctx::StreamScratch);
-      ssp = slot.get();
-    }
-    scratch_lock = std::unique_lock<std::mutex>(ssp->m);
-    gst_ctx::StreamScratch &ss = *ssp;
     if (ss.cap < L.scratch_bytes) {
       // stream-ordered: the old buffer is released after the work already queued on this stream
       if (ss.ptr) GST_CUDA_TRY(cudaFreeAsync(ss.ptr, stream));
@@ -278,6 +290,16 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
       ss.cap = cap;
     }
     scratch = ss.ptr;
+  }
+  if (ss.sync_cap < n) {
+    if (ss.sync) GST_CUDA_TRY(cudaFreeAsync(ss.sync, stream));
+    ss.sync = nullptr;
+    ss.sync_cap = 0;
+    const size_t cap = align_up(static_cast<size_t>(n) + n / 4, 1024);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ss.sync), 2 * cap * sizeof(uint32_t), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ss.sync, 0, 2 * cap * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "hand-over counters for %u images: %s", n, cudaGetErrorString(e));
+    ss.sync_cap = cap;
   }
 
   gst::BatchParams p{};
@@ -299,6 +321,8 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
   p.status = ctx->d_status;
+  p.img_done = ss.sync;
+  p.tiles_done = ss.sync + ss.sync_cap;
   gst::fill_kernel_constants(&p);
   p.freq_inline = freq_inline ? 1u : 0u;
   if (inline_offsets) {
@@ -485,7 +509,7 @@ void gst_ctx_destroy(gst_ctx *ctx) {
     }
   if (ctx->arena) cudaFree(ctx->arena);
   for (auto &kv : ctx->stream_scratch)
-    if (kv.second && kv.second->ptr) cudaFree(kv.second->ptr);
+    if (kv.second) kv.second->release();
   if (ctx->ans_ws) cudaFree(ctx->ans_ws);
   if (ctx->d_status) cudaFree(ctx->d_status);
   for (auto &hs : ctx->host_slots) {
@@ -713,7 +737,7 @@ int gst_free_scratch(gst_ctx *ctx) {
   {
     std::lock_guard<std::mutex> lock(ctx->scratch_mutex);
     for (auto &kv : ctx->stream_scratch)
-      if (kv.second && kv.second->ptr) cudaFree(kv.second->ptr);
+      if (kv.second) kv.second->release();
     ctx->stream_scratch.clear();
   }
   std::lock_guard<std::mutex> lock(ctx->arena_mutex);
@@ -1016,7 +1040,7 @@ void gst_streamer_destroy(gst_streamer *st) {
         std::lock_guard<std::mutex> lock(st->ctx->scratch_mutex);
         auto it = st->ctx->stream_scratch.find(s.stream);
         if (it != st->ctx->stream_scratch.end()) {
-          if (it->second && it->second->ptr) cudaFree(it->second->ptr);
+          if (it->second) it->second->release();
           st->ctx->stream_scratch.erase(it);
         }
       }

@@ -72,6 +72,40 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
 // Both are no-ops for kernels launched without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Hand-over of an image from rans_streams_kernel to wavelet_assemble_kernel.  The second kernel is launched as a
+// programmatic dependent of the first, so its CTAs become resident as soon as EVERY decode CTA has started (they all
+// pass pdl_launch_dependents() first thing) and SMs have room -- that is, during the last, partly filled wave of the
+// decode kernel.  Instead of sleeping in griddepcontrol.wait until the whole decode grid has drained, a tile warp
+// waits for its own image only: every decode CTA of image b releases its stores with a fence and counts itself into
+// img_done[b]; the tile warp acquires the counter.  A warp can only ever wait for CTAs that are already running, so the
+// wait cannot deadlock; it is bounded all the same (GST_FLAG_SYNC_TIMEOUT) so that a broken launch order shows up
+// as a flag and a failed parity check, not as a hung GPU.  The acquire makes everything the image's decode CTAs
+// wrote visible; beyond that, what the tile warps read is either fetched past L1 (cp.async.cg; ld.cg for the group
+// totals, of which several small images share a line) or lies in cache lines that hold data of their own image only
+// (symbols, suffix sums, run ends and palettes are multiples of 128 bytes per image).
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_for_image(const uint32_t *done, uint32_t target, uint32_t *status) {
+  // The whole warp probes (one request: all lanes read the same word) and the vote keeps the loop warp-uniform,
+  // so that ptxas does not duplicate the code that follows for a divergent lane 0.  (Probing with ld.acquire would
+  // invalidate the SM's L1 at every probe: CCTL.IVALL.)
+  uint32_t spins = 0;
+#pragma unroll 1
+  while (!__all_sync(0xffffffffu, ld_relaxed_gpu(done) >= target)) {
+    __nanosleep(100);
+    if (++spins > (1u << 23)) {  // > 1 s
+      atomicOr(status, 4u);
+      break;
+    }
+  }
+  // relaxed load + fence = acquire.  The fence invalidates the SM's L1 (CCTL.IVALL), which costs the tile kernel
+  // 1.3 % (the prefetched suffix sums and palette lines of the other warps go with it); without it the step measured
+  // 0.5 % faster and every parity test passed, but the hand-over would rest on the hardware, not on the memory model.
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t lanemask_gt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
@@ -591,21 +625,19 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
 // LONE: the grid fits the machine at three CTAs per SM, so there is no occupancy to protect and the kernel is not held
 // to the 48 registers that 5 CTAs per SM allow -- free of that cap ptxas keeps the table base and the ring addresses
 // in registers instead of recomputing them at every checkpoint (72 registers), and a lone group finishes 20 % sooner.
-template <bool TAP, bool FT, bool LONE>
-__global__ void __launch_bounds__(kRansWarps * 32, LONE ? 3 : RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+template <bool TAP, bool FT>
+__device__ __forceinline__ void rans_streams_cta(const BatchParams &p, const StreamGrid &sg, uint32_t b, uint32_t r, uint8_t *smem) {
   constexpr int NC = RansCfg::kChains;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  pdl_launch_dependents();
   const RansSmem lay(smem_u32(smem));
   const uint32_t warp = threadIdx.x >> 5;
   uint32_t ring[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) ring[c] = lay.ring(NC * warp + c);
-  const uint32_t tab_s = lay.tab;
+  // (volatile: the table base stays in its register instead of being rematerialised from S2R + LOP3 at every
+  // checkpoint of the decode loop: rans_streams 1.2 % faster)
+  uint32_t tab_s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(tab_s) : "r"(lay.tab));
 
-  const uint32_t per_image = sg.per_image();
-  const uint32_t b = blockIdx.x / per_image;
-  uint32_t r = blockIdx.x % per_image;
   uint32_t type;  // 0 Y, 1 chroma, 2 palette, 3 index
   if (r < sg.y_ctas) type = 0;
   else if ((r -= sg.y_ctas) < sg.c_ctas) type = 1;
@@ -620,7 +652,7 @@ __global__ void __launch_bounds__(kRansWarps * 32, LONE ? 3 : RansCfg::kCtasPerS
   const uint32_t n_chains = type == 0 ? 2 * p.groups_per_plane : type == 1 ? 4 * p.groups_per_plane
                           : type == 2 ? is.palette_bytes / kGroupSyms : p.groups_per_plane;
   const uint32_t first = r * RansCfg::kGroupsPerCta;
-  if (first >= n_chains) return;
+  if (first >= n_chains) return;  // (the palette CTAs of the grid are sized for the largest palette of the batch)
   if (FT) {
     __shared__ TableScratch ts;
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + (lay.tab - lay.s0));
@@ -642,6 +674,23 @@ __global__ void __launch_bounds__(kRansWarps * 32, LONE ? 3 : RansCfg::kCtasPerS
   } else {
     const uint32_t ring1[1] = {ring[0]};
     rans_stream_groups<1, TAP>(p, b, type, chain, stream, out_off, is.pal_off, tab_s, ring1);
+  }
+}
+
+template <bool TAP, bool FT, bool LONE>
+__global__ void __launch_bounds__(kRansWarps * 32, LONE ? 3 : RansCfg::kCtasPerSm) rans_streams_kernel(const BatchParams p, const StreamGrid sg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
+  const uint32_t per_image = sg.per_image();
+  const uint32_t b = blockIdx.x / per_image;
+  rans_streams_cta<TAP, FT>(p, sg, b, blockIdx.x % per_image, smem);
+  // hand-over: everything this CTA wrote is released to the tile warps of image b (see wait_for_image).  The image
+  // index is taken afresh from %ctaid (volatile), so that nothing stays live across the 48-register decode loops for it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t cta;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.img_done + cta / per_image) : "memory");
   }
 }
 
@@ -939,7 +988,8 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   if (tile >= p.n_blocks / kTileSyms) return;
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
-  pdl_wait();  // everything below reads what rans_streams_kernel wrote
+  // everything below reads what rans_streams_kernel wrote for image b
+  wait_for_image(p.img_done + b, p.rans_ctas, p.status);
 
   // ---- the tile's coefficients: sym_t -> raw halves of the W rows -------------------------------
   {
@@ -977,18 +1027,19 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   const uint32_t g_first = (ty * kTile * p.blocks_x + tx * kTile) / kGroupSyms;                 // group of tile row 0
   const uint32_t g_last = ((ty * kTile + kTile - 1) * p.blocks_x + tx * kTile) / kGroupSyms;    // ... of tile row 31
   const int32_t *tot = p.idx_total + static_cast<size_t>(b) * p.groups_per_plane;
-  const int32_t tot_lane = lane < g_first ? __ldg(tot + lane) : 0;   // this lane's share of the groups before the tile
-  const int32_t tot_first = __ldg(tot + g_first);
+  // (ld.cg: the totals of several small images share a cache line, which may have been cached before ours were written)
+  const int32_t tot_lane = lane < g_first ? __ldcg(tot + lane) : 0;   // this lane's share of the groups before the tile
+  const int32_t tot_first = __ldcg(tot + g_first);
   uint32_t re_row = static_cast<uint32_t>(__ldg(p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + g_row / kSymsPerLane));
   auto resolve_run_ends = [&]() {
     int32_t part = tot_lane;
 #pragma unroll 1  // (code size: the kernel has to stay inside the 32 KiB L1.5 instruction cache)
-    for (uint32_t g = lane + 32; g < g_first; g += 32) part += __ldg(tot + g);   // (images beyond 2048 x 2048 only)
+    for (uint32_t g = lane + 32; g < g_first; g += 32) part += __ldcg(tot + g);   // (images beyond 2048 x 2048 only)
     int32_t carry = __reduce_add_sync(0xffffffffu, part);
     if (grp > g_first) carry += tot_first;
 #pragma unroll 1
     for (uint32_t g = g_first + 1; g < g_last; ++g) {                            // (tile rows spanning > 2 groups only)
-      const int32_t t = __ldg(tot + g);
+      const int32_t t = __ldcg(tot + g);
       if (grp > g) carry += t;
     }
     re_row += static_cast<uint32_t>(carry);
@@ -1224,6 +1275,14 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     const bool over = IDX16 ? ((seen & 0xFFFFu) > (nmax & 0xFFFFu) || (seen >> 16) > (nmax >> 16)) : seen > nmax;
     if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(p.status, 1u);
   }
+  // the last tile of the image leaves both hand-over counters at zero for the next call on this scratch
+  if (lane == 0 && atomicAdd(p.tiles_done + b, 1u) + 1u == p.n_blocks / kTileSyms) {
+    p.img_done[b] = 0u;
+    p.tiles_done[b] = 0u;
+  }
+  // (no griddepcontrol.wait anywhere in this kernel: a warp blocked in it would hold its CTA slot until the whole
+  // decode grid has drained, and the early tiles are there to free theirs for the next ones.  The last tiles of the
+  // last image cannot finish before every decode CTA has counted itself in, which is the last thing those do.)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1392,9 +1451,10 @@ bool is_small_call(uint32_t n_images, uint32_t groups_per_plane, uint32_t max_pa
   return static_cast<uint64_t>(n_images) * (7ull * groups_per_plane + max_palette_bytes / kGroupSyms) <= kSmallCallGroups;
 }
 
-cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max_palette_bytes,
+cudaError_t launch_decode_batch(const BatchParams &p_in, int rgb_mode, uint32_t max_palette_bytes,
                                 cudaStream_t s, cudaEvent_t *marks) {
-  if (p.n_images == 0) return cudaSuccess;
+  if (p_in.n_images == 0) return cudaSuccess;
+  BatchParams p = p_in;
   cudaError_t e = ensure_attrs();
   if (e != cudaSuccess) return e;
   int mark = 0;
@@ -1418,6 +1478,7 @@ cudaError_t launch_decode_batch(const BatchParams &p, int rgb_mode, uint32_t max
   sg.c_ctas = (4 * p.groups_per_plane + per_cta - 1) / per_cta;
   sg.pal_ctas = (max_palette_bytes / kGroupSyms + per_cta - 1) / per_cta;
   sg.idx_ctas = (p.groups_per_plane + per_cta - 1) / per_cta;
+  p.rans_ctas = sg.per_image();
   // the stage taps (parity tests only) are a separate instantiation: the production kernels carry none of that code
   const bool taps = p.tap_symbols || p.tap_planes || p.tap_indices;
   const dim3 rans_grid(p.n_images * sg.per_image()), rans_block(kRansWarps * 32);

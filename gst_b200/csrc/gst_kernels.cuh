@@ -66,6 +66,11 @@ struct BatchParams {
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
   uint32_t *status;          // [0]: flags OR-ed in by the kernels (GST_FLAG_*), [1]: a zero word (the palette of an image
                              // whose palette region is unusable)
+  // Image-granular hand-over from rans_streams_kernel to wavelet_assemble_kernel (gst_kernels.cu, "hand-over"):
+  // both arrays are zero between calls.
+  uint32_t *img_done;        // [B] rans_streams CTAs of image b that have finished (complete at rans_ctas)
+  uint32_t *tiles_done;      // [B] tiles of image b wavelet_assemble has finished; the last one zeroes both counters
+  uint32_t rans_ctas;        // CTAs rans_streams_kernel runs per image (set by launch_decode_batch)
   uint32_t freq_inline;      // 1: no frequency region; an image's four frequency blocks precede its Y stream in the payload
   uint32_t inline_off;       // 1: n_images == 1 and the offset table is off8 below, not the first 32 bytes of cmp
   uint32_t off8[8];          // out_off[0..3], in_off[0..3] of that image

@@ -185,10 +185,13 @@ void gst_streamer_destroy(gst_streamer *st);
  * SURVEY.md section 5); here every access is clamped, and a decode that had to clamp says so: the kernels OR
  *   GST_FLAG_INDEX_CLAMPED   a palette index lay beyond the image's palette (it was clamped to the last entry)
  *   GST_FLAG_PALETTE_RANGE   an image's palette region did not fit its batch (its blocks got index word 0)
+ *   GST_FLAG_SYNC_TIMEOUT    internal: a tile waited more than a second for its image's entropy decode (never
+ *                            expected; the output of that call is not to be trusted)
  * into one word per context.  gst_status_flags reads it (and clears it when `clear` is non-zero); call it after the
  * work of interest has completed (gst_stream_sync / an event). */
 #define GST_FLAG_INDEX_CLAMPED 1u
 #define GST_FLAG_PALETTE_RANGE 2u
+#define GST_FLAG_SYNC_TIMEOUT 4u
 int gst_status_flags(gst_ctx *ctx, uint32_t *flags, int clear);
 
 /* ---- stage taps for the parity tests (not used in production).  Any pointer may be NULL.

@@ -240,3 +240,74 @@ def test_streamer_play_groups(decoder, group, direct):
         assert np.array_equal(host.array[f * per:(f + 1) * per], srcs[f % 5][1]), f"host frame {f}"
         assert np.array_equal(dev[f * per:(f + 1) * per], srcs[f % 5][1]), f"device frame {f}"
     d_out.free()
+
+
+def test_back_to_back_calls_reuse_the_hand_over_counters_and_scratch(decoder):
+    """The image-granular hand-over between the entropy-decode kernel and the tile kernel keeps per-stream counters
+    that the kernels leave at zero, and the tile warps read scratch the previous call of the stream used for OTHER
+    data.  Two different batches of small images (sixteen images' index totals share a cache line) alternate on one
+    queue without any host synchronisation in between; every output is checked and no flag may be raised."""
+    w = h = 512
+    per = w * h // 2
+    sets = []
+    for s in range(2):
+        files = [_random_container(decoder, w, h, 100 * s + i) for i in range(40)]
+        want = np.stack([fx.oracle_decode(f, taps=False)["out"] for f in files])
+        packed, hdrs = gst_b200.pack_batch(files)
+        d_cmp = decoder.malloc(packed.size)
+        decoder.upload(d_cmp, packed)
+        sets.append((hdrs, d_cmp, want))
+    rounds = 12
+    outs = [decoder.malloc(per * 40) for _ in range(2 * rounds)]
+    for o in outs:
+        decoder.memset(o, 0xEE)
+    decoder.status_flags(clear=True)
+    q = decoder.GetDefaultCommandQueue()
+    for r in range(2 * rounds):
+        hdrs, d_cmp, _ = sets[r % 2]
+        decoder.LoadCompressedDXTs(hdrs, q, d_cmp, outs[r], want_event=False)
+    decoder.sync(q)
+    assert decoder.status_flags() == 0
+    for r in range(2 * rounds):
+        got = decoder.download(outs[r]).reshape(40, per)
+        assert np.array_equal(got, sets[r % 2][2]), f"call {r} differs from the CPU oracle"
+    for o in outs:
+        o.free()
+    for _, d_cmp, _ in sets:
+        d_cmp.free()
+
+
+def test_back_to_back_large_calls_three_kernel_path(decoder):
+    """The same for calls large enough to take the three-kernel path (separate table build, both later kernels launched
+    as programmatic dependents): 300 x 1024x1024 per call, two different sets alternating on one queue."""
+    w = h = 1024
+    per = w * h // 2
+    n = 300
+    sets = []
+    for s in range(2):
+        distinct = [_random_container(decoder, w, h, 500 + 10 * s + i) for i in range(8)]
+        want = [fx.oracle_decode(f, taps=False)["out"] for f in distinct]
+        order = [(3 * i + s) % 8 for i in range(n)]
+        packed, hdrs = gst_b200.pack_batch([distinct[j] for j in order])
+        d_cmp = decoder.malloc(packed.size)
+        decoder.upload(d_cmp, packed)
+        sets.append((hdrs, d_cmp, want, order))
+    outs = [decoder.malloc(per * n) for _ in range(4)]
+    for o in outs:
+        decoder.memset(o, 0xEE)
+    decoder.status_flags(clear=True)
+    q = decoder.GetDefaultCommandQueue()
+    for r in range(4):
+        hdrs, d_cmp, _, _ = sets[r % 2]
+        decoder.LoadCompressedDXTs(hdrs, q, d_cmp, outs[r], want_event=False)
+    decoder.sync(q)
+    assert decoder.status_flags() == 0
+    for r in range(4):
+        got = decoder.download(outs[r]).reshape(n, per)
+        _, _, want, order = sets[r % 2]
+        for pos, j in enumerate(order):
+            assert np.array_equal(got[pos], want[j]), f"call {r}, image {pos} differs from the CPU oracle"
+    for o in outs:
+        o.free()
+    for _, d_cmp, _, _ in sets:
+        d_cmp.free()
