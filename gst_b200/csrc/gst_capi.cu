@@ -49,6 +49,7 @@ constexpr int kNumWorkStreams = 4;  // gpu/gpu.h:49 kMaxNumWorkQueues
 // (measured on the GPU boxes), so 8 workers are what it takes to keep a PCIe 5 x16 link (~55 GB/s) fed.
 constexpr int kHostSlots = 8;
 constexpr size_t kQuantum = 512;    // the reference's sub-buffer alignment quantum
+constexpr size_t kSyncPoolWords = 1 << 18;  // hand-over counters a stream hands out before it zeroes its pool again (1 MiB)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -72,16 +73,17 @@ struct gst_ctx {
                    // regrow the buffer in between
     uint8_t *ptr = nullptr;
     size_t cap = 0;
-    // hand-over counters of the calls on this stream (BatchParams::img_done / tiles_done): 2 x sync_cap words, zero
-    // whenever no call is running (the kernels leave them so); also used by calls that take their scratch from the arena
+    // hand-over counters of the calls on this stream (BatchParams::img_done), also used by calls that take their
+    // scratch from the arena: a zeroed pool every call cuts its n words from; when the pool is used up it is
+    // zeroed again in stream order (once per ~hundreds of calls), so no kernel ever has to reset a counter
     uint32_t *sync = nullptr;
-    size_t sync_cap = 0;
+    size_t sync_cap = 0, sync_used = 0;
     void release() {
       if (ptr) cudaFree(ptr);
       if (sync) cudaFree(sync);
       ptr = nullptr;
       sync = nullptr;
-      cap = sync_cap = 0;
+      cap = sync_cap = sync_used = 0;
     }
   };
   std::mutex scratch_mutex;
@@ -100,6 +102,7 @@ struct gst_ctx {
     size_t cap_in = 0, cap_out = 0;
   } host_slots[kHostSlots];
   std::atomic<bool> direct_upload{false};  // gst_ctx_set_direct_upload
+  size_t sync_pool_words = kSyncPoolWords;  // (GST_SYNC_POOL_WORDS in the environment: tests make the pool wrap)
   // [0]: status flags the kernels OR into (gst_status_flags), [1]: a zero word
   uint32_t *d_status = nullptr;
   // workspace of the standalone rANS decode / encode entry points (grow-only, one call at a time)
@@ -227,7 +230,7 @@ int layout_batch(const gst_header *hdrs, uint32_t n, BatchLayout *L) {
   // palette indices < 2^16 everywhere -> the per-block index suffix sums are kept as u16
   L->idx16 = max_pal / 4 <= 65536u;
   L->idx_off = off;     off += align_up(static_cast<size_t>(n) * N * (L->idx16 ? 2 : 4), kQuantum);
-  L->total_off = off;   off += align_up(static_cast<size_t>(n) * L->groups_per_plane * 4, kQuantum);
+  L->total_off = off;   off += align_up(static_cast<size_t>(n) * gst::idx_total_stride(L->groups_per_plane) * 4, kQuantum);
   L->run_off = off;     off += align_up(static_cast<size_t>(n) * (N / gst::kSymsPerLane) * 4, kQuantum);
   L->scratch_bytes = off;
   return GST_OK;
@@ -291,15 +294,24 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
     }
     scratch = ss.ptr;
   }
-  if (ss.sync_cap < n) {
-    if (ss.sync) GST_CUDA_TRY(cudaFreeAsync(ss.sync, stream));
-    ss.sync = nullptr;
-    ss.sync_cap = 0;
-    const size_t cap = align_up(static_cast<size_t>(n) + n / 4, 1024);
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ss.sync), 2 * cap * sizeof(uint32_t), stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ss.sync, 0, 2 * cap * sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "hand-over counters for %u images: %s", n, cudaGetErrorString(e));
-    ss.sync_cap = cap;
+  uint32_t *img_done = nullptr;
+  if (n > 1) {
+    const size_t need = align_up(static_cast<size_t>(n), 32);  // (whole cache lines per call)
+    if (ss.sync_cap < need) {
+      if (ss.sync) GST_CUDA_TRY(cudaFreeAsync(ss.sync, stream));
+      ss.sync = nullptr;
+      ss.sync_cap = ss.sync_used = 0;
+      const size_t cap = std::max<size_t>(4 * need, ctx->sync_pool_words);
+      cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ss.sync), cap * sizeof(uint32_t), stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(ss.sync, 0, cap * sizeof(uint32_t), stream);
+      if (e != cudaSuccess) return fail(GST_ERR_NOMEM, "hand-over counters for %u images: %s", n, cudaGetErrorString(e));
+      ss.sync_cap = cap;
+    } else if (ss.sync_used + need > ss.sync_cap) {
+      GST_CUDA_TRY(cudaMemsetAsync(ss.sync, 0, ss.sync_cap * sizeof(uint32_t), stream));  // after every earlier call of the stream
+      ss.sync_used = 0;
+    }
+    img_done = ss.sync + ss.sync_used;
+    ss.sync_used += need;
   }
 
   gst::BatchParams p{};
@@ -321,8 +333,7 @@ int decode_batch(gst_ctx *ctx, const gst_header *hdrs, uint32_t n, cudaStream_t 
   p.run_end = reinterpret_cast<int32_t *>(scratch + L.run_off);
   p.out = static_cast<uint8_t *>(out_dev);
   p.status = ctx->d_status;
-  p.img_done = ss.sync;
-  p.tiles_done = ss.sync + ss.sync_cap;
+  p.img_done = img_done;
   gst::fill_kernel_constants(&p);
   p.freq_inline = freq_inline ? 1u : 0u;
   if (inline_offsets) {
@@ -464,6 +475,10 @@ int gst_ctx_create(int device, gst_ctx **out) {
   gst_ctx *ctx = new (std::nothrow) gst_ctx;
   if (!ctx) return fail(GST_ERR_NOMEM, "out of host memory");
   ctx->device = device;
+  if (const char *v = getenv("GST_SYNC_POOL_WORDS")) {
+    const long w = atol(v);
+    if (w >= 32) ctx->sync_pool_words = static_cast<size_t>(w);
+  }
   for (auto &s : ctx->streams) {
     e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     if (e != cudaSuccess) {

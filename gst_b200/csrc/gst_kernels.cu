@@ -80,9 +80,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // img_done[b]; the tile warp acquires the counter.  A warp can only ever wait for CTAs that are already running, so the
 // wait cannot deadlock; it is bounded all the same (GST_FLAG_SYNC_TIMEOUT) so that a broken launch order shows up
 // as a flag and a failed parity check, not as a hung GPU.  The acquire makes everything the image's decode CTAs
-// wrote visible; beyond that, what the tile warps read is either fetched past L1 (cp.async.cg; ld.cg for the group
-// totals, of which several small images share a line) or lies in cache lines that hold data of their own image only
-// (symbols, suffix sums, run ends and palettes are multiples of 128 bytes per image).
+// wrote visible; beyond that, what the tile warps read is either fetched past L1 (cp.async.cg) or lies in cache
+// lines that hold data of their own image only (symbols, suffix sums, run ends and palettes are multiples of 128
+// bytes per image, the group totals are padded to that: idx_total_stride).
 __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -614,7 +614,7 @@ __device__ __forceinline__ void rans_stream_groups(const BatchParams &p, uint32_
       if (lane >= d) inc += n;
     }
     p.run_end[static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + (group + c) * kLanes + lane] = static_cast<int32_t>(inc);
-    if (lane == 31) p.idx_total[static_cast<size_t>(b) * p.groups_per_plane + group + c] = static_cast<int32_t>(inc);
+    if (lane == 31) p.idx_total[static_cast<size_t>(b) * idx_total_stride(p.groups_per_plane) + group + c] = static_cast<int32_t>(inc);
   }
 }
 
@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(kRansWarps * 32, LONE ? 3 : RansCfg::kCtasPerS
   rans_streams_cta<TAP, FT>(p, sg, b, blockIdx.x % per_image, smem);
   // hand-over: everything this CTA wrote is released to the tile warps of image b (see wait_for_image).  The image
   // index is taken afresh from %ctaid (volatile), so that nothing stays live across the 48-register decode loops for it
+  if (p.img_done == nullptr) return;  // (single image: the tile kernel waits for the grid, see wavelet_assemble_kernel)
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t cta;
@@ -988,8 +989,11 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   if (tile >= p.n_blocks / kTileSyms) return;
   const uint32_t tiles_x = p.blocks_x / kTile;
   const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
-  // everything below reads what rans_streams_kernel wrote for image b
-  wait_for_image(p.img_done + b, p.rans_ctas, p.status);
+  // everything below reads what rans_streams_kernel wrote for image b.  A single image is complete when the decode
+  // grid is, and griddepcontrol.wait is the cheaper wait then (the hand-over costs a lone image 2 us: a fence at the
+  // end of its decode CTAs, a probe and a fence here)
+  if (p.img_done != nullptr) wait_for_image(p.img_done + b, p.rans_ctas, p.status);
+  else pdl_wait();
 
   // ---- the tile's coefficients: sym_t -> raw halves of the W rows -------------------------------
   {
@@ -1026,20 +1030,19 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
   const uint32_t grp = g_row / kGroupSyms;
   const uint32_t g_first = (ty * kTile * p.blocks_x + tx * kTile) / kGroupSyms;                 // group of tile row 0
   const uint32_t g_last = ((ty * kTile + kTile - 1) * p.blocks_x + tx * kTile) / kGroupSyms;    // ... of tile row 31
-  const int32_t *tot = p.idx_total + static_cast<size_t>(b) * p.groups_per_plane;
-  // (ld.cg: the totals of several small images share a cache line, which may have been cached before ours were written)
-  const int32_t tot_lane = lane < g_first ? __ldcg(tot + lane) : 0;   // this lane's share of the groups before the tile
-  const int32_t tot_first = __ldcg(tot + g_first);
+  const int32_t *tot = p.idx_total + static_cast<size_t>(b) * idx_total_stride(p.groups_per_plane);
+  const int32_t tot_lane = lane < g_first ? __ldg(tot + lane) : 0;   // this lane's share of the groups before the tile
+  const int32_t tot_first = __ldg(tot + g_first);
   uint32_t re_row = static_cast<uint32_t>(__ldg(p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + g_row / kSymsPerLane));
   auto resolve_run_ends = [&]() {
     int32_t part = tot_lane;
 #pragma unroll 1  // (code size: the kernel has to stay inside the 32 KiB L1.5 instruction cache)
-    for (uint32_t g = lane + 32; g < g_first; g += 32) part += __ldcg(tot + g);   // (images beyond 2048 x 2048 only)
+    for (uint32_t g = lane + 32; g < g_first; g += 32) part += __ldg(tot + g);   // (images beyond 2048 x 2048 only)
     int32_t carry = __reduce_add_sync(0xffffffffu, part);
     if (grp > g_first) carry += tot_first;
 #pragma unroll 1
     for (uint32_t g = g_first + 1; g < g_last; ++g) {                            // (tile rows spanning > 2 groups only)
-      const int32_t t = __ldcg(tot + g);
+      const int32_t t = __ldg(tot + g);
       if (grp > g) carry += t;
     }
     re_row += static_cast<uint32_t>(carry);
@@ -1275,14 +1278,11 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
     const bool over = IDX16 ? ((seen & 0xFFFFu) > (nmax & 0xFFFFu) || (seen >> 16) > (nmax >> 16)) : seen > nmax;
     if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(p.status, 1u);
   }
-  // the last tile of the image leaves both hand-over counters at zero for the next call on this scratch
-  if (lane == 0 && atomicAdd(p.tiles_done + b, 1u) + 1u == p.n_blocks / kTileSyms) {
-    p.img_done[b] = 0u;
-    p.tiles_done[b] = 0u;
-  }
-  // (no griddepcontrol.wait anywhere in this kernel: a warp blocked in it would hold its CTA slot until the whole
+  // (no griddepcontrol.wait on the hand-over path: a warp blocked in it would hold its CTA slot until the whole
   // decode grid has drained, and the early tiles are there to free theirs for the next ones.  The last tiles of the
-  // last image cannot finish before every decode CTA has counted itself in, which is the last thing those do.)
+  // last image cannot finish before every decode CTA has counted itself in, which is the last thing those do.  The
+  // counters are not reset here either -- an atomic whose result a warp has to wait for keeps its slot busy for a
+  // microsecond per tile: every call gets fresh, zeroed counters from the host side, gst_capi.cu.)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1479,6 +1479,7 @@ cudaError_t launch_decode_batch(const BatchParams &p_in, int rgb_mode, uint32_t 
   sg.pal_ctas = (max_palette_bytes / kGroupSyms + per_cta - 1) / per_cta;
   sg.idx_ctas = (p.groups_per_plane + per_cta - 1) / per_cta;
   p.rans_ctas = sg.per_image();
+  if (p.n_images == 1) p.img_done = nullptr;  // no hand-over for a lone image
   // the stage taps (parity tests only) are a separate instantiation: the production kernels carry none of that code
   const bool taps = p.tap_symbols || p.tap_planes || p.tap_indices;
   const dim3 rans_grid(p.n_images * sg.per_image()), rans_block(kRansWarps * 32);

@@ -61,15 +61,14 @@ struct BatchParams {
   void *idx_s;               // [B][N] u16 or u32, transposed like sym_t: sum of the index deltas after block i in its 256-block run
   uint32_t idx16;            // 1: idx_s holds u16 (every palette <= 65536 entries), 0: u32
   int32_t *run_end;          // [B][N/256] group-local inclusive index prefix at the end of every run
-  int32_t *idx_total;        // [B][N/8192] sum of the index deltas of each index group
+  int32_t *idx_total;        // [B][idx_total_stride(N/8192)] sum of the index deltas of each index group
   // outputs
   uint8_t *out;              // DXT1: B * 8N bytes;  RGB8: B * 48N bytes
   uint32_t *status;          // [0]: flags OR-ed in by the kernels (GST_FLAG_*), [1]: a zero word (the palette of an image
                              // whose palette region is unusable)
   // Image-granular hand-over from rans_streams_kernel to wavelet_assemble_kernel (gst_kernels.cu, "hand-over"):
-  // both arrays are zero between calls.
-  uint32_t *img_done;        // [B] rans_streams CTAs of image b that have finished (complete at rans_ctas)
-  uint32_t *tiles_done;      // [B] tiles of image b wavelet_assemble has finished; the last one zeroes both counters
+  uint32_t *img_done;        // [B] rans_streams CTAs of image b that have finished (complete at rans_ctas); zero when the
+                             // call starts; NULL: no hand-over (single image), the tile kernel waits for the whole grid
   uint32_t rans_ctas;        // CTAs rans_streams_kernel runs per image (set by launch_decode_batch)
   uint32_t freq_inline;      // 1: no frequency region; an image's four frequency blocks precede its Y stream in the payload
   uint32_t inline_off;       // 1: n_images == 1 and the offset table is off8 below, not the first 32 bytes of cmp
@@ -80,6 +79,9 @@ struct BatchParams {
   int8_t *tap_planes;        // [B][6][N] raster planes (codec/decoder.cpp:280)
   int32_t *tap_indices;      // [B][N] final palette indices (codec/decoder.cpp:302)
 };
+
+// words per image in BatchParams::idx_total: whole 128-byte lines, so that no cache line holds totals of two images
+__host__ __device__ inline uint32_t idx_total_stride(uint32_t groups_per_plane) { return (groups_per_plane + 31u) & ~31u; }
 
 inline void fill_kernel_constants(BatchParams *p) {
   auto ph = [](int v) { return (static_cast<uint32_t>(v) & 0xFFFFu) * 65537u; };

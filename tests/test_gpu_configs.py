@@ -242,11 +242,14 @@ def test_streamer_play_groups(decoder, group, direct):
     d_out.free()
 
 
-def test_back_to_back_calls_reuse_the_hand_over_counters_and_scratch(decoder):
-    """The image-granular hand-over between the entropy-decode kernel and the tile kernel keeps per-stream counters
-    that the kernels leave at zero, and the tile warps read scratch the previous call of the stream used for OTHER
-    data.  Two different batches of small images (sixteen images' index totals share a cache line) alternate on one
-    queue without any host synchronisation in between; every output is checked and no flag may be raised."""
+def test_back_to_back_calls_reuse_the_hand_over_counters_and_scratch(monkeypatch):
+    """The image-granular hand-over between the entropy-decode kernel and the tile kernel takes its counters from a
+    zeroed per-stream pool that is zeroed again, in stream order, when it is used up, and the tile warps read scratch
+    the previous call of the stream used for OTHER data.  Two different batches of small images (sixteen images' index
+    totals share a cache line) alternate on one queue without any host synchronisation in between, on a context whose
+    pool lasts four calls; every output is checked and no flag may be raised."""
+    monkeypatch.setenv("GST_SYNC_POOL_WORDS", "256")
+    decoder = gst_b200.Decoder(0)
     w = h = 512
     per = w * h // 2
     sets = []
@@ -275,6 +278,7 @@ def test_back_to_back_calls_reuse_the_hand_over_counters_and_scratch(decoder):
         o.free()
     for _, d_cmp, _ in sets:
         d_cmp.free()
+    decoder.close()
 
 
 def test_back_to_back_large_calls_three_kernel_path(decoder):
