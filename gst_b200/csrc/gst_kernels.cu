@@ -83,28 +83,25 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // wrote visible; beyond that, what the tile warps read is either fetched past L1 (cp.async.cg) or lies in cache
 // lines that hold data of their own image only (symbols, suffix sums, run ends and palettes are multiples of 128
 // bytes per image, the group totals are padded to that: idx_total_stride).
-__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
   uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void wait_for_image(const uint32_t *done, uint32_t target, uint32_t *status) {
   // The whole warp probes (one request: all lanes read the same word) and the vote keeps the loop warp-uniform,
-  // so that ptxas does not duplicate the code that follows for a divergent lane 0.  (Probing with ld.acquire would
-  // invalidate the SM's L1 at every probe: CCTL.IVALL.)
+  // so that ptxas does not duplicate the code that follows for a divergent lane 0.  An acquire LOAD is a strong load
+  // plus an invalidation of the SM's L1 (LDG.E.STRONG.GPU + CCTL.IVALL); a relaxed probe followed by
+  // fence.acq_rel.gpu would add a MEMBAR.ALL.GPU, on which the tile warps were found waiting 10 % of their time.
   uint32_t spins = 0;
 #pragma unroll 1
-  while (!__all_sync(0xffffffffu, ld_relaxed_gpu(done) >= target)) {
+  while (!__all_sync(0xffffffffu, ld_acquire_gpu(done) >= target)) {
     __nanosleep(100);
     if (++spins > (1u << 23)) {  // > 1 s
       atomicOr(status, 4u);
       break;
     }
   }
-  // relaxed load + fence = acquire.  The fence invalidates the SM's L1 (CCTL.IVALL), which costs the tile kernel
-  // 1.3 % (the prefetched suffix sums and palette lines of the other warps go with it); without it the step measured
-  // 0.5 % faster and every parity test passed, but the hand-over would rest on the hardware, not on the memory model.
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t lanemask_gt() {
   uint32_t m;
