@@ -886,16 +886,16 @@ __device__ __forceinline__ void col_offsets(uint32_t c, uint32_t (&off)[8]) {
   for (int s = 0; s < 8; ++s) off[s] = ((((c >> 2) ^ s) & 7) << 4) + (c & 3) * 4;
 }
 
-// One level (LEN = 2..16) of all three plane pairs: row pass with lane = (plane pair, row), then
-// column pass with lane = (plane pair, column).
-template <int LEN>
-__device__ __forceinline__ void low_level_p(uint32_t w_s, uint32_t lane, uint32_t k10, const ShiftK &sk) {
-  constexpr int ITEMS = 3 * LEN;
+// One level (LEN = 2..16) of NP plane pairs (all three, or pair pl0 alone): row pass with lane = (plane pair, row),
+// then column pass with lane = (plane pair, column).
+template <int LEN, int NP = 3>
+__device__ __forceinline__ void low_level_p(uint32_t w_s, uint32_t lane, uint32_t k10, const ShiftK &sk, uint32_t pl0 = 0) {
+  constexpr int ITEMS = NP * LEN;
 #pragma unroll 1  // (code size: the kernel has to stay inside the 32 KiB L1.5 instruction cache)
   for (int base = 0; base < ITEMS; base += 32) {
     const uint32_t item = base + lane;
     if (item < ITEMS) {
-      const uint32_t wp = w_s + (item / LEN) * kWPlane, r = item % LEN;
+      const uint32_t wp = w_s + (NP == 1 ? pl0 : item / LEN) * kWPlane, r = item % LEN;
       uint32_t v[LEN];
       load_row<LEN>(wp, r, v, k10);
       // low band: the previous level's result (bias kBias) in rows < LEN / 2, raw coefficients below
@@ -908,7 +908,7 @@ __device__ __forceinline__ void low_level_p(uint32_t w_s, uint32_t lane, uint32_
   for (int base = 0; base < ITEMS; base += 32) {
     const uint32_t item = base + lane;
     if (item < ITEMS) {
-      const uint32_t wp = w_s + (item / LEN) * kWPlane, c = item % LEN;
+      const uint32_t wp = w_s + (NP == 1 ? pl0 : item / LEN) * kWPlane, c = item % LEN;
       uint32_t off[8];
       col_offsets(c, off);
       uint32_t v[LEN];
@@ -1283,6 +1283,169 @@ __global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Stages 4 + 5 for calls of so few tiles that the machine is empty (a single image up to 4096 x 4096): one CTA of
+// THREE warps per tile instead of one warp.  wavelet_assemble_kernel is built for throughput -- a warp takes a tile
+// through ~4000 instructions on its own, 10-14 us when it has an SM sub-partition to itself; here warp w
+// transforms plane pair w (the pairs are independent until the assembly), the CTA meets at one barrier, and the
+// eight 4-row slabs of the assembly are dealt out to the warps (slabs w, w + 3, w + 6).  The suffix sums and the
+// palette words of a warp's slabs are requested before the wavelet, so the assembly finds them in registers.  Same
+// arithmetic, same helpers, same scratch layout as wavelet_assemble_kernel; DXT1 output only (RGB8 and the parity
+// taps keep the one-warp kernel).
+constexpr int kSplitWarps = 3;
+constexpr uint32_t kSplitMaxTiles = 7 * 148;  // the grid has to fit the machine in one wave (7 CTAs per SM)
+
+template <bool IDX16>
+__global__ void __launch_bounds__(kSplitWarps * 32, 7) wavelet_assemble_split_kernel(const BatchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_s = smem_u32(smem);
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  const uint32_t tiles_x = p.blocks_x / kTile;
+  const uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
+  if (p.img_done != nullptr) wait_for_image(p.img_done + b, p.rans_ctas, p.status);
+  else pdl_wait();
+
+  // this warp's plane pair: sym_t -> raw halves of the W rows (as in wavelet_assemble_kernel)
+  const uint32_t wp = w_s + warp * kWPlane;
+  {
+    const uint32_t tq = tile & 7;
+    const uint8_t *src0 = p.sym_t + static_cast<size_t>(b) * 6 * p.n_blocks + static_cast<size_t>(tile >> 3) * (2 * kGroupSyms) +
+                          static_cast<size_t>(warp) * p.groups_per_plane * (2 * kGroupSyms);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t pc = lane + 32 * i, r = pc >> 2, j = pc & 3;
+      cp_async16(wchunk(wp, r, 4 + j), src0 + (2 * (r & 7) + (j >> 1)) * 1024 + (4 * tq + (r >> 3)) * 32 + (j & 1) * 16);
+    }
+    cp_async_commit();
+  }
+  const uint4 out_off = p.inline_off ? make_uint4(p.off8[0], p.off8[1], p.off8[2], p.off8[3]) : __ldg(reinterpret_cast<const uint4 *>(p.cmp) + b);
+
+  // run ends of the 32 tile rows (lane = tile row) and the carry of the earlier index groups, as in the one-warp kernel
+  const size_t img_block0 = static_cast<size_t>(b) * p.n_blocks;
+  const uint32_t g_row = (ty * kTile + lane) * p.blocks_x + tx * kTile;
+  const uint32_t grp = g_row / kGroupSyms;
+  const uint32_t g_first = (ty * kTile * p.blocks_x + tx * kTile) / kGroupSyms;
+  const uint32_t g_last = ((ty * kTile + kTile - 1) * p.blocks_x + tx * kTile) / kGroupSyms;
+  const int32_t *tot = p.idx_total + static_cast<size_t>(b) * idx_total_stride(p.groups_per_plane);
+  int32_t part = 0;
+  for (uint32_t g = lane; g < g_first; g += 32) part += __ldg(tot + g);
+  const int32_t tot_first = __ldg(tot + g_first);
+  uint32_t re_row = static_cast<uint32_t>(__ldg(p.run_end + static_cast<size_t>(b) * (p.n_blocks / kSymsPerLane) + g_row / kSymsPerLane));
+
+  // suffix sums of this warp's slabs k = warp, warp + 3, warp + 6 (transposed layout: see sfx_ptr in the one-warp kernel)
+  const uint32_t gidx0 = (ty * kTile + (lane >> 3)) * p.blocks_x + tx * kTile + 4 * (lane & 7);
+  const uint32_t slab_stride = 4 * p.blocks_x;
+  uint4 sfx[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint32_t k = warp + 3 * i;
+    sfx[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (k < 8) {
+      const uint32_t gidx = gidx0 + k * slab_stride, h = gidx >> 4;
+      const uint32_t e32 = (gidx & ~8191u) + ((h & 15u) << 9) + (h & 0x1F0u) + (gidx & 15u);
+      const uint8_t *sp = reinterpret_cast<const uint8_t *>(p.idx_s) + (IDX16 ? 2 : 4) * (img_block0 + e32);
+      if (IDX16) {
+        const uint2 sv = __ldg(reinterpret_cast<const uint2 *>(sp));
+        sfx[i] = make_uint4(sv.x, sv.y, 0u, 0u);
+      } else {
+        sfx[i] = __ldg(reinterpret_cast<const uint4 *>(sp));
+      }
+    }
+  }
+
+  uint32_t k10 = 0x10101010u;
+  asm volatile("" : "+r"(k10));
+  cp_async_wait_group<0>();
+  __syncwarp();
+  {
+    int32_t carry = __reduce_add_sync(0xffffffffu, part);
+    if (grp > g_first) carry += tot_first;
+    for (uint32_t g = g_first + 1; g < g_last; ++g) {
+      const int32_t t = __ldg(tot + g);
+      if (grp > g) carry += t;
+    }
+    re_row += static_cast<uint32_t>(carry);
+  }
+
+  // palette words of this warp's slabs: requested now, used after the barrier
+  uint32_t words[3][4];
+  uint32_t nmax, seen = 0;
+  {
+    const uint32_t palette_bytes = out_off.w - out_off.z;
+    const uint32_t pal_off = out_off.z - 7u * p.n_blocks * b - 6u * p.n_blocks;
+    const uint32_t n_entries = palette_bytes / 4;
+    const bool pal_ok = static_cast<uint64_t>(pal_off) + palette_bytes <= p.palette_cap && n_entries > 0;
+    const uint32_t *pal = pal_ok ? reinterpret_cast<const uint32_t *>(p.palette + pal_off) : p.status + 1;
+    nmax = pal_ok ? n_entries - 1 : 0u;
+    if (!pal_ok && threadIdx.x == 0) atomicOr(p.status, 2u);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t k = warp + 3 * i;
+      const uint32_t re = __shfl_sync(0xffffffffu, re_row, (4 * k + (lane >> 3)) & 31);
+      uint32_t u[4];
+      if (IDX16) {
+        u[0] = (re + sfx[i].x) & 0xFFFFu; u[1] = (re + (sfx[i].x >> 16)) & 0xFFFFu;
+        u[2] = (re + sfx[i].y) & 0xFFFFu; u[3] = (re + (sfx[i].y >> 16)) & 0xFFFFu;
+      } else {
+        u[0] = re + sfx[i].x; u[1] = re + sfx[i].y; u[2] = re + sfx[i].z; u[3] = re + sfx[i].w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k < 8) seen = max(seen, u[j]);
+        words[i][j] = k < 8 ? __ldg(pal + min(u[j], nmax)) : 0u;
+      }
+    }
+  }
+
+  // stage 4 for this warp's pair
+  const ShiftK sk{p.kc[0], p.kc[1], p.kc[3], p.kc[4], p.kc[5], p.kc[6]};
+  low_level_p<2, 1>(w_s, lane, k10, sk, warp);
+  low_level_p<4, 1>(w_s, lane, k10, sk, warp);
+  low_level_p<8, 1>(w_s, lane, k10, sk, warp);
+  low_level_p<16, 1>(w_s, lane, k10, sk, warp);
+  {
+    uint32_t v[32];
+    load_row<32>(wp, lane, v, k10);
+    inverse_lift_p<32, kRaw>(v, lane < 16 ? pk(2048) : pk(2048 + kBias - kRaw), sk);
+    store_row<32>(wp, lane, v);
+  }
+  __syncwarp();
+  {
+    uint32_t off[8];
+    col_offsets(lane, off);
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = lds32(wp + off[i & 7] + i * 128);
+    inverse_lift_p<32, kBias>(v, pk(2048), sk);
+    const uint32_t kx = warp == 0 ? ph(128 + kBY) : warp == 1 ? ph(128 + kBO) : ph(128 + kBG);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sts32(wp + off[i & 7] + i * 128, (v[i] & 0x00FF00FFu) ^ kx);
+  }
+  __syncthreads();
+
+  // stage 5 for this warp's slabs
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint32_t k = warp + 3 * i;
+    if (k < 8) {
+      const uint32_t src = wchunk(w_s, 4 * k + (lane >> 3), lane & 7);
+      uint32_t Y[4], CO[4], CG[4];
+      ld4(src, Y); ld4(src + kWPlane, CO); ld4(src + 2 * kWPlane, CG);
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[2 * j] = pack565_p(Y[j], CO[j], CG[j], sk);
+        o[2 * j + 1] = words[i][j];
+      }
+      uint8_t *dst = p.out + (img_block0 + gidx0 + k * slab_stride) * 8;
+      st_global_cs_v4(dst, o[0], o[1], o[2], o[3]);
+      st_global_cs_v4(dst + 16, o[4], o[5], o[6], o[7]);
+    }
+  }
+  if (__any_sync(0xffffffffu, seen > nmax) && lane == 0) atomicOr(p.status, 1u);
+}
+
+// ---------------------------------------------------------------------------------------
 // Standalone decode of [u32 end_offset[n_groups]][groups] with 1..32 interleaved lanes and a
 // single table: the `ans_decode` kernel of ans/ans_decode.cl:76-95 as driven by
 // ans/ans_ocl.cpp:159-345.  Output: group * n_lanes * 256 + lane * 256 + position.
@@ -1496,6 +1659,14 @@ cudaError_t launch_decode_batch(const BatchParams &p_in, int rgb_mode, uint32_t 
   if (p.n_images > 65535u) return cudaErrorInvalidValue;  // grid.y; gst_capi.cu pages larger batches
   const dim3 grid((p.n_blocks / kTileSyms + kWaWarps - 1) / kWaWarps, p.n_images), block(kWaWarps * 32);
   auto launch = [&](auto kern) { return launch_kernel(kern, grid, block, kWaSmem, s, pdl, p); };
+  if (!rgb_mode && !taps && static_cast<uint64_t>(p.n_images) * (p.n_blocks / kTileSyms) <= kSplitMaxTiles) {
+    // so few tiles that every one can have a CTA of three warps to itself, all resident at once
+    const dim3 sgrid(p.n_blocks / kTileSyms, p.n_images), sblock(kSplitWarps * 32);
+    e = p.idx16 ? launch_kernel(wavelet_assemble_split_kernel<true>, sgrid, sblock, kWarpWork, s, pdl, p)
+                : launch_kernel(wavelet_assemble_split_kernel<false>, sgrid, sblock, kWarpWork, s, pdl, p);
+    if (e != cudaSuccess) return e;
+    return stamp();
+  }
   const int variant = (rgb_mode ? 1 : 0) | (taps ? 2 : 0) | (p.idx16 ? 4 : 0);
   switch (variant) {
     case 0: e = launch(wavelet_assemble_kernel<0, false, false>); break;
