@@ -277,7 +277,8 @@ class Decoder:
     KERNEL_NAMES = ("build_tables", "rans_streams", "wavelet_assemble")
 
     def status_flags(self, clear=True):
-        """gst_status_flags: bit 0 = a palette index was clamped, bit 1 = a palette region was out of range."""
+        """gst_status_flags: bit 0 = a palette index was clamped, bit 1 = a palette region was out of range,
+        bit 2 = the kernels' internal hand-over timed out (never expected)."""
         f = C.c_uint32()
         check(lib().gst_status_flags(self.ctx, C.byref(f), 1 if clear else 0))
         return f.value
