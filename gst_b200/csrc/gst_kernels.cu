@@ -971,12 +971,14 @@ __device__ __forceinline__ uint32_t pack565_p(uint32_t Y, uint32_t CO, uint32_t 
 //   assembly: 4 DXT1 blocks (or 64 RGB8 texels) per lane and 4-row slab, coalesced 16-byte
 //             stores; palette index = run_end - S.  The index / palette loads of the next slab
 //             are in flight while a slab is assembled, those of slab 0 during the wavelet.
-constexpr int kWaWarps = 2;
-constexpr int kWaSmem = kWaWarps * kWarpWork;  // 24576
+// One tile warp per CTA: the warps share nothing, and a CTA of two held its slot until the slower one was done
+// (2.529 -> 2.513 ms per step; three per CTA: 2.545).
+constexpr int kWaWarps = 1;
+constexpr int kWaSmem = kWaWarps * kWarpWork;  // 12288
 
 // IDX16: the index suffix sums are u16 (every palette of the batch has <= 65536 entries), else u32.
 template <int RGB, bool TAP, bool IDX16>
-__global__ void __launch_bounds__(kWaWarps * 32, 9) wavelet_assemble_kernel(const BatchParams p) {
+__global__ void __launch_bounds__(kWaWarps * 32, 18 / kWaWarps) wavelet_assemble_kernel(const BatchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
