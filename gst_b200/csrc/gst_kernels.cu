@@ -778,22 +778,29 @@ __device__ __forceinline__ uint32_t lift_even_p(uint32_t S, uint32_t HP, uint32_
   return fma_sub_from(Qc, S);
 }
 // d[2x+1] = h[x] + (d[2x] + d[2x+2]) / 2.  The d operands are computed values (bias kBias); cH = pk(-bias of H).
+// LAST: the result goes straight to the (char) truncation, which keeps the low byte of each half only.  With a bias of
+// H that is a multiple of 256 the correction cH cannot change that byte and is not added at all; and the bit the shift
+// carries from the high half into bit 15 of the low half is left in: it is not in the low byte, and the low half stays
+// below 2^15 + 2^13 + 2^13, so it carries nothing back into the high half either.
+template <bool LAST = false>
 __device__ __forceinline__ uint32_t lift_odd_p(uint32_t H, uint32_t EP, uint32_t EN, uint32_t cH, const ShiftK &sk) {
   const uint32_t T = fma_add(EP, EN);                     // t + 2^13
   const uint32_t T2 = trunc_fix<1, 8192>(T, sk);
+  if (LAST) return shr_add<1>(T2, H);
   return shr_add<1>(T2 & 0xFFFEFFFEu, H) + cH;            // h + trunc(t / 2) + 4096 - bias of H
 }
 // 1-D inverse 5/3 lifting of v = [low half | high half] in registers, codec/inverse_wavelet.cl:28-64
 // (NormalizeIndex mirror resolved at compile time).  HB = bias of the high half; the result has bias kBias.
-template <int LEN, int HB>
+template <int LEN, int HB, bool LAST = false>
 __device__ __forceinline__ void inverse_lift_p(uint32_t (&v)[LEN], uint32_t cD, const ShiftK &sk) {
+  static_assert(!LAST || HB % 256 == 0, "the dropped correction must be a multiple of 256 per half");
   constexpr int MID = LEN / 2;
   uint32_t o[LEN];
 #pragma unroll
   for (int x = 0; x < MID; ++x) o[2 * x] = lift_even_p<HB>(v[x], v[MID + (x == 0 ? 0 : x - 1)], v[MID + x], cD, sk);
 #pragma unroll
   for (int x = 0; x < MID; ++x)
-    o[2 * x + 1] = lift_odd_p(v[MID + x], o[2 * x], o[(2 * x + 2 == LEN) ? 2 * x : 2 * x + 2], pk(-HB), sk);
+    o[2 * x + 1] = lift_odd_p<LAST>(v[MID + x], o[2 * x], o[(2 * x + 2 == LEN) ? 2 * x : 2 * x + 2], pk(-HB), sk);
 #pragma unroll
   for (int i = 0; i < LEN; ++i) v[i] = o[i];
 }
@@ -1167,7 +1174,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 18 / kWaWarps) wavelet_assemble
       uint32_t v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = lds32(wp + off[i & 7] + i * 128);
-      inverse_lift_p<32, kBias>(v, pk(2048), sk);
+      inverse_lift_p<32, kBias, true>(v, pk(2048), sk);
       // (char) truncation: low byte of (x + 4096) = x mod 256; ^ 0x80 makes it (int8) x + 128
       const uint32_t kx = pl == 0 ? ph(128 + kBY) : pl == 1 ? ph(128 + kBO) : ph(128 + kBG);
 #pragma unroll
@@ -1421,7 +1428,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 7) wavelet_assemble_split_ke
     uint32_t v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = lds32(wp + off[i & 7] + i * 128);
-    inverse_lift_p<32, kBias>(v, pk(2048), sk);
+    inverse_lift_p<32, kBias, true>(v, pk(2048), sk);
     const uint32_t kx = warp == 0 ? ph(128 + kBY) : warp == 1 ? ph(128 + kBO) : ph(128 + kBG);
 #pragma unroll
     for (int i = 0; i < 32; ++i) sts32(wp + off[i & 7] + i * 128, (v[i] & 0x00FF00FFu) ^ kx);
