@@ -68,7 +68,8 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
 }
 // Programmatic dependent launch: the next kernel of the stream may be scheduled once every CTA of this one has
-// passed pdl_launch_dependents(); it blocks in pdl_wait() until this kernel has completed and its writes are visible.
+// passed pdl_launch_dependents().  pdl_wait() blocks until this whole kernel has completed and its writes are visible;
+// the tile kernels of multi-image calls use the finer, per-image wait below instead (wait_for_image).
 // Both are no-ops for kernels launched without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -658,7 +659,7 @@ __device__ __forceinline__ void rans_streams_cta(const BatchParams &p, const Str
     TableScratch &ts = *reinterpret_cast<TableScratch *>(smem + (lay.tab - lay.s0) + 4 * kTableSize);
     build_table_cta(reinterpret_cast<const uint16_t *>(freq_block(p, b, type, is.in_off[0])), tab, tab, ts);
   } else {
-    pdl_wait();  // (the tables come from build_tables_kernel)
+    pdl_wait();  // (the tables come from build_tables_batch_kernel)
     load_table(tab_s, p.tables + (4ull * b + type) * kTableSize, threadIdx.x, kRansWarps * 32);
   }
   __syncthreads();
@@ -992,7 +993,7 @@ __global__ void __launch_bounds__(kWaWarps * 32, 18 / kWaWarps) wavelet_assemble
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_s = smem_u32(smem) + warp * kWarpWork;
-  // grid = (tile pairs of an image, images): no division by the tiles per image
+  // grid = (tiles of an image, images): no division by the tiles per image
   const uint32_t b = blockIdx.y;
   const uint32_t tile = blockIdx.x * kWaWarps + warp;
   if (tile >= p.n_blocks / kTileSyms) return;
